@@ -1,0 +1,455 @@
+#!/usr/bin/env python
+"""bench.py -- pairwise OT distances / second on the PILOT patient-distance hot path.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--workload c2]
+
+One "step" = one pass of the whole hot path (proportion histogram -> median centroids -> cdist
+-> all-pairs OT -> dense S x S matrix) over one synthetic cohort.  The default workload is
+BASELINE.json configs[1] ("c2": 1M cells, 50-dim embedding, 30 cell types, 100 samples,
+stabilised Sinkhorn reg = 0.1 on one B200).  Prints ONE JSON line (rank 0).
+
+  value     -- problems/s with the inputs already resident in HBM (CUDA-event timed)
+  e2e       -- the same metric through the public API pilot_b200.tl.wasserstein_distance(adata)
+               with HOST inputs (pinned embedding), H2D/D2H inside the timed region
+  roofline  -- the dominant kernel of the step against the measured peak
+  cpu_baseline -- the oracle port of the reference's CPU path on the box's host cores (N = 1 only)
+  kernels   -- extra: C5-shaped (K = 64, 20 000 samples) slices of the two pair kernels
+
+N > 1 (torchrun, one rank per GPU): weak scaling -- the cohort grows so every rank keeps 10^4 OT
+problems (S_N = ceil(100 sqrt(N))), the pair space is partitioned over the ranks and assembled
+with one NCCL all-gather inside the timed region; time = max over ranks.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import math
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "pairwise OT distances/sec (exact EMD & Sinkhorn) at 1/2/4/8 B200"
+UNIT = "OT problems/s"
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return float(d["hbm_gbs"]), "measured"
+    return 6650.0, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.idx = gpu_index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                 "-i", str(self.idx)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            f = [x.strip() for x in r.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"),
+                               f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# ---------------------------------------------------------------------------------------------
+# workload
+# ---------------------------------------------------------------------------------------------
+def workload_shape(name: str, n_gpus: int):
+    from pilot_b200 import synth
+    n, d, k, s, seed = synth.CONFIGS[name]
+    s_n = int(math.ceil(s * math.sqrt(n_gpus))) if n_gpus > 1 else s
+    return n, d, k, s_n, seed
+
+
+def make_workload(name: str, n_gpus: int):
+    from pilot_b200 import synth
+    n, d, k, s, seed = workload_shape(name, n_gpus)
+    X, obs = synth.make_cells(n, d, k, s, seed, labels="categorical")
+    return X, obs, (n, d, k, s)
+
+
+REG = {"c1": None, "c2": 0.1, "c3": 0.1, "c4": 0.01}
+
+
+# ---------------------------------------------------------------------------------------------
+# reference arm / cpu baseline: the oracle port of the reference's CPU path
+# ---------------------------------------------------------------------------------------------
+def cpu_reference_step(X, obs, reg, rows):
+    """One bounded pass of the reference's CPU path (oracle port; the reference itself is verbatim-
+    exec'd when /root/reference is mounted): stages 1-2 in full, stage 3 on the first `rows` rows
+    of the ordered pair matrix through the reference's Python loop semantics (NumPy
+    sinkhorn_stabilized restatement / C network simplex, one core, per-call overhead included)."""
+    import pandas as pd
+    from oracle import pilot_oracle as po
+    from oracle import ref_exec
+    annot = obs[["cell_types", "sampleID", "status"]].copy()
+    annot.columns = ["cell_type", "sampleID", "status"]
+    data = pd.DataFrame(X)
+    t0 = time.perf_counter()
+    if ref_exec.available():
+        ref = ref_exec.load()
+        props = ref.Cluster_Representations(annot)
+        t1 = time.perf_counter()
+        dis, _ = ref.cost_matrix(annot, data, "cosine")
+    else:
+        props = po.cluster_representations(annot)
+        t1 = time.perf_counter()
+        dis, _ = po.cost_matrix(annot, data, "cosine")
+    t2 = time.perf_counter()
+    ids = list(props.keys())
+    S = len(ids)
+    M = dis / dis.max()
+    rows = min(rows, S)
+    out = np.zeros((rows, S))
+    for i in range(rows):
+        for j in range(S):
+            if reg is None:
+                out[i, j] = po.emd2(props[ids[i]], props[ids[j]], M)
+            else:
+                out[i, j] = po.sinkhorn2_np(props[ids[i]], props[ids[j]], M, reg)
+    t3 = time.perf_counter()
+    full = (t1 - t0) + (t2 - t1) + (t3 - t2) * S / rows
+    return dict(t_props=t1 - t0, t_cost=t2 - t1, t_pairs_sample=t3 - t2, rows=rows, S=S,
+                t_step_extrapolated=full, problems_per_s=S * S / full,
+                kind="reference+port" if ref_exec.available() else "port")
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    X, obs, (n, d, k, s) = make_workload(args.workload, 1)
+    reg = REG[args.workload]
+    rows = 4
+    with tempfile.TemporaryDirectory() as tmp:
+        cwd = os.getcwd(); os.chdir(tmp)
+        try:
+            for _ in range(args.warmup):
+                cpu_reference_step(X, obs, reg, 1)
+            t0 = time.perf_counter()
+            res = [cpu_reference_step(X, obs, reg, rows) for _ in range(args.steps)]
+            wall = time.perf_counter() - t0
+        finally:
+            os.chdir(cwd)
+    step = float(np.mean([r["t_step_extrapolated"] for r in res]))
+    value = s * s / step
+    sample = (f"stages 1-2 in full ({n} cells); stage 3 on the first {rows} of {s} rows "
+              f"({rows * s} ordered problems, NumPy sinkhorn_stabilized restatement in the reference's Python "
+              f"loop), extrapolated x{s}/{rows}; measured wall per step {wall / args.steps:.2f}s")
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": step * 1e3, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": f"{args.workload}: {n} cells x {d} dims, {k} types, {s} samples, "
+                                   f"Sinkhorn reg={reg}" if reg else f"{args.workload}: exact EMD"},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": 1, "kind": res[0]["kind"], "sample": sample},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------------------------
+# B200 arm
+# ---------------------------------------------------------------------------------------------
+class DeviceStep:
+    """The hot path with device-resident inputs, stage by stage (what tl.wasserstein_distance runs)."""
+
+    def __init__(self, X, obs, reg):
+        import torch
+        from pilot_b200 import tl
+        self.torch = torch
+        self.reg = reg
+        annot = obs[["cell_types", "sampleID", "status"]].copy()
+        annot.columns = ["cell_type", "sampleID", "status"]
+        self.lab = tl._Labels(annot, "cell_type", "sampleID")      # codes on device + perms
+        self.X = tl._embedding_to_device(X)
+        self.launches = 0
+
+    def run(self, timers=None):
+        from pilot_b200 import ops, pairs
+        torch = self.torch
+        lab = self.lab
+
+        def mark(name):
+            if timers is not None:
+                ev = torch.cuda.Event(enable_timing=True)
+                ev.record()
+                timers.append((name, ev))
+
+        mark("start")
+        counts_raw, first_ct, first_smp = ops.hist(lab.ct_dev, lab.sm_dev, lab.K_raw, lab.S_raw)
+        mark("hist")
+        props, counts = ops.props_finalize(counts_raw, lab.perm_k_dev, lab.perm_s_dev, lab.n, 0.2, True)
+        mark("props")
+        _, cent64_raw = ops.centroid_median(self.X, lab.ct_dev, lab.K_raw)
+        mark("median")
+        cent64 = cent64_raw.index_select(0, lab.perm_k_dev.long()).contiguous()
+        cost, cost_norm, _ = ops.cdist(cent64, "cosine")
+        mark("cdist")
+        dense = pairs.all_pairs(props, cost_norm, "unreg" if self.reg is None else "reg",
+                                self.reg if self.reg is not None else 0.1)
+        mark("pairs")
+        return dense, props, cost
+
+
+# kernel launches of ONE DeviceStep.run() (my kernels only; memsets and torch's index_select excluded):
+# hist_init + hist (2), colsum + finalize (2), median 4 x (hist + scan) + final (9), cdist prep/pair/norm (3),
+# sinkhorn setup + batched + reference-form redo (3) or emd (1), unpack (1)
+def launches_per_step(reg):
+    return 2 + 2 + 9 + 3 + (3 if reg is not None else 1) + 1
+
+
+def pair_kernel_slices(peak_fp64):
+    """C5-shaped slices (K = 64, S = 20 000): the two pair kernels alone, device resident."""
+    import torch
+    from oracle import pilot_oracle as po
+    from pilot_b200 import _lib, ops, synth
+    S, K = 20_000, 64
+    P, M = synth.make_pairs(S, K, seed=5)
+    Pd, Md = torch.from_numpy(P).cuda(), torch.from_numpy(M).cuda()
+    res = {}
+
+    def timed(fn, reps=2):
+        fn()
+        torch.cuda.synchronize()
+        best = None
+        for _ in range(reps):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(); out = fn(); e1.record(); torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1)
+            best = ms if best is None else min(best, ms)
+        return best, out
+
+    # Sinkhorn: first 96 rows x 20 000 columns (ordered problems)
+    rows = 96
+    rng = ops.make_range(rows * S, _lib.PAIRS_FULL)
+    ms, out = timed(lambda: ops.sinkhorn_pairs(Pd, Md, 0.1, rng, want_info=True))
+    iters = out[1].sum().item()
+    flops = float(iters) * 4 * K * K
+    res["sinkhorn_c5_slice"] = {
+        "problems": rows * S, "ms": ms, "problems_per_s": rows * S / (ms * 1e-3),
+        "mean_iters": iters / (rows * S), "algorithmic_tflops": flops / (ms * 1e-3) / 1e12,
+        "fp64_fma_peak_tflops": peak_fp64, "frac_of_fp64_peak": flops / (ms * 1e-3) / 1e12 / peak_fp64}
+    # exact EMD: first 1 000 000 pairs of the upper triangle
+    n_emd = 1_000_000
+    rng = ops.make_range(n_emd, _lib.PAIRS_UPPER)
+    rng.total = n_emd
+    ms, out = timed(lambda: ops.emd_pairs(Pd, Md, rng, want_info=True))
+    # algorithmic work of the REFERENCE algorithm on the same kind of input: 3A + 2U + 2C
+    _, _, st = po.emd_rows(P[:24], M, 0, 24, return_stats=True)
+    ops_per_problem = (3 * st["arcs_priced"] + 2 * st["pot_updates"] + 2 * st["cycle_steps"]) / (24 * 24)
+    res["emd_c5_slice"] = {
+        "problems": n_emd, "ms": ms, "pairs_per_s": n_emd / (ms * 1e-3),
+        "mean_pivots": out[2].float().mean().item(),
+        "reference_algorithm_fp64_ops_per_problem": ops_per_problem,
+        "algorithmic_tflops": ops_per_problem * n_emd / (ms * 1e-3) / 1e12,
+        "fp64_fma_peak_tflops": peak_fp64,
+        "frac_of_fp64_peak": ops_per_problem * n_emd / (ms * 1e-3) / 1e12 / peak_fp64}
+    return res
+
+
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+    from pilot_b200 import ops, synth, tl
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    n_gpus = world
+
+    X, obs, (n, d, k, s) = make_workload(args.workload, n_gpus)
+    reg = REG[args.workload]
+    hbm_peak, peak_kind = load_peaks()
+
+    tmp = tempfile.mkdtemp()
+    os.chdir(tmp)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---------------- device-resident timing ("value") ----------------
+    step = DeviceStep(X, obs, reg)
+    for _ in range(args.warmup):
+        step.run()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        dense, props, cost = step.run()
+    e1.record()
+    barrier()
+    ms_total = e0.elapsed_time(e1)
+    clocks = sampler.stop() if rank == 0 else None
+    t = torch.tensor([ms_total], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_step = t.item() / args.steps
+    value = s * s / (ms_step * 1e-3)
+
+    # ---------------- per-kernel breakdown + roofline of the dominant kernel ----------------
+    stage_ms = {}
+    for _ in range(3):
+        timers = []
+        step.run(timers)
+        torch.cuda.synchronize()
+        for (n0, ev0), (n1, ev1) in zip(timers[:-1], timers[1:]):
+            stage_ms.setdefault(n1, []).append(ev0.elapsed_time(ev1))
+    stage_ms = {kname: float(np.mean(v)) for kname, v in stage_ms.items()}
+    elt = X.dtype.itemsize
+    alg_bytes = {"hist": n * 8 + s * k * 8, "median": n * d * elt + n * 4 + k * d * elt}
+    dominant = max(stage_ms, key=stage_ms.get)
+    roofline = None
+    if dominant in alg_bytes:
+        ach = alg_bytes[dominant] / (stage_ms[dominant] * 1e-3) / 1e9
+        roofline = {"kernel": dominant, "bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s",
+                    "frac": ach / hbm_peak, "traffic": None, "peak_source": peak_kind,
+                    "algorithmic_bytes": alg_bytes[dominant], "ms": stage_ms[dominant]}
+
+    # ---------------- end to end through the public API ----------------
+    pinned = torch.empty(X.shape, dtype=torch.float32 if X.dtype == np.float32 else torch.float64, pin_memory=True)
+    Xp = pinned.numpy()
+    Xp[...] = X
+    kw = dict(emb_matrix="X_PCA", clusters_col="cell_types", sample_col="sampleID", status="status",
+              regularized="unreg" if reg is None else "reg", reg=reg if reg is not None else 0.1)
+    def api_step():
+        adata = synth.FakeAnnData(obs, obsm={"X_PCA": Xp})
+        tl.wasserstein_distance(adata, **kw)
+        return adata
+    for _ in range(max(1, min(args.warmup, 3))):
+        api_step()
+    barrier()
+    e2e_steps = max(1, min(args.steps, 10))
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        adata = api_step()
+    torch.cuda.synchronize()
+    t_e2e = (time.perf_counter() - t0) / e2e_steps
+    te = torch.tensor([t_e2e], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    t_e2e = te.item()
+    h2d = n * 8 + X.nbytes + (k + s) * 4
+    d2h = s * s * 8 + s * k * 8 + k * k * 8 + (k + s) * 8
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": n_gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": f"{args.workload} (BASELINE configs[1]): {n} cells x {d}-dim {X.dtype} embedding, "
+                                   f"{k} cell types, {s} samples, cosine cost, "
+                                   + (f"stabilised Sinkhorn reg={reg}, all {s * s} ordered pairs" if reg is not None
+                                      else "exact EMD"),
+                       "l2": "inputs (embedding %.0f MB) larger than the 126 MB L2; no flush" % (X.nbytes / 1e6),
+                       "multi_gpu": "pair space block-partitioned over ranks, one NCCL all-gather per step; "
+                                    "stages 1-2 replicated; samples scale as ceil(100*sqrt(N))"},
+            "clocks": clocks,
+            "e2e": {"value": s * s / t_e2e, "unit": UNIT, "h2d_bytes_per_step": int(h2d),
+                    "d2h_bytes_per_step": int(d2h), "ms_per_step": t_e2e * 1e3,
+                    "api": "pilot_b200.tl.wasserstein_distance(adata) with categorical obs and a pinned host embedding"},
+            "gpu_launches": launches_per_step(reg) * args.steps,
+            "stage_ms": stage_ms, "roofline": roofline}
+
+    if n_gpus == 1:
+        # pipe peaks (roofline denominators the driver does not measure) and the pair kernels at C5 shape
+        peaks = {"fp64_fma_tflops": ops.pipe_peak(0), "fp32_fma_tflops": ops.pipe_peak(1),
+                 "fp64_dmma_tflops": ops.pipe_peak(2)}
+        line["pipe_peaks"] = peaks
+        try:
+            line["kernels"] = pair_kernel_slices(peaks["fp64_fma_tflops"])
+        except Exception as exc:  # keep the headline line even if the extra slices fail
+            line["kernels"] = {"error": repr(exc)}
+        if roofline is None:
+            # dominant stage is the pair kernel: FP64 FMA pipe bound
+            iters = None
+            line["roofline"] = {"kernel": dominant, "bound": "fp64-fma", "achieved": None, "peak": peaks["fp64_fma_tflops"],
+                                "unit": "TFLOP/s", "frac": None, "traffic": None, "ms": stage_ms[dominant]}
+        cb = cpu_reference_step(X, obs, reg, 4)
+        line["cpu_baseline"] = {
+            "value": cb["problems_per_s"], "unit": UNIT, "cores": 1, "kind": cb["kind"],
+            "sample": f"stages 1-2 in full ({cb['t_props']:.2f}s + {cb['t_cost']:.2f}s); stage 3 on the first "
+                      f"{cb['rows']} of {cb['S']} rows ({cb['t_pairs_sample']:.2f}s), extrapolated x{cb['S']}/{cb['rows']}"}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="c2", choices=["c1", "c2", "c3", "c4"])
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

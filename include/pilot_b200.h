@@ -1,0 +1,175 @@
+/*
+ * pilot_b200.h -- C ABI of the B200-native PILOT patient-distance hot path.
+ *
+ * The reference (CostaLab/PILOT, pilotpy 2.0.6) has no FFI/plugin interface: the
+ * boundary is the Python function surface of pilotpy/tools/Trajectory.py plus
+ * the adata.uns contract.  Each entry point below replaces the
+ * *native arithmetic* that one reference statement reaches, and is what a
+ * ctypes binding inside pilotpy would call.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer owned by the caller unless its name
+ *     starts with h_ ; the library allocates nothing persistent
+ *   - scratch comes from a caller-provided workspace (pilot_workspace_bytes)
+ *   - `stream` is a cudaStream_t (CUstream) passed as void*; all work is
+ *     asynchronous on it
+ *   - return value: 0 = OK, <0 = bad argument, >0 = CUDA error code;
+ *     pilot_last_error() returns a thread-local message
+ *   - no torch types, no C++ types
+ */
+#ifndef PILOT_B200_H
+#define PILOT_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PILOT_B200_ABI_VERSION 1
+
+/* element types of the embedding handed to pilot_centroid_median */
+#define PILOT_F32 0
+#define PILOT_F64 1
+
+/* pdist metrics accepted by pilot_cdist (scipy.spatial.distance.pdist names) */
+#define PILOT_METRIC_COSINE      0
+#define PILOT_METRIC_EUCLIDEAN   1
+#define PILOT_METRIC_SQEUCLIDEAN 2
+#define PILOT_METRIC_CITYBLOCK   3
+#define PILOT_METRIC_CHEBYSHEV   4
+#define PILOT_METRIC_CORRELATION 5
+
+/* how a linear problem index g maps to a sample pair (i, j) */
+#define PILOT_PAIRS_FULL  0   /* g = i*S + j, all S*S ordered pairs incl. diagonal     */
+#define PILOT_PAIRS_UPPER 1   /* strictly upper triangle, row-major, S*(S-1)/2 pairs    */
+
+/* per-problem status written by the *_pairs kernels */
+#define PILOT_ST_CONVERGED 0  /* Sinkhorn: err <= stopThr ; EMD: optimal               */
+#define PILOT_ST_MAXITER   1  /* Sinkhorn: numItermax reached ; EMD: pivot cap reached */
+#define PILOT_ST_NUMERIC   2  /* Sinkhorn: NaN roll-back (POT "Numerical errors")      */
+#define PILOT_ST_UNBOUNDED 3  /* EMD only                                              */
+
+/* workspace kinds for pilot_workspace_bytes */
+#define PILOT_WS_MEDIAN   0
+#define PILOT_WS_SINKHORN 1
+#define PILOT_WS_EMD      2
+
+/*
+ * Partition of the linear pair space [0, total) over `nranks` processes:
+ * blocks of `block` consecutive problems are dealt round-robin; rank r owns
+ * blocks r, r+nranks, ...  Its packed output holds its blocks back to back.
+ * nranks=1, rank=0 means "everything".  
+ */
+typedef struct {
+    int64_t total;   /* S*S (FULL) or S*(S-1)/2 (UPPER), or fewer to truncate */
+    int64_t block;   /* problems per block (>=1) */
+    int32_t nranks;
+    int32_t rank;
+    int32_t mode;    /* PILOT_PAIRS_* */
+    int32_t reserved;
+} pilot_pair_range;
+
+int         pilot_abi_version(void);
+const char *pilot_last_error(void);
+/* number of problems `range` assigns to range->rank */
+int64_t     pilot_range_count(const pilot_pair_range *range);
+size_t      pilot_workspace_bytes(int kind, int64_t n, int K, int S, int D);
+
+/*
+ * (1) Proportion counting -- replaces the pandas unique/value_counts/boolean-mask
+ * scans of Cluster_Representations, Trajectory.py:402-425.
+ * ct_code[i] in [0,K), smp_code[i] in [0,S) are arbitrary (not necessarily
+ * first-appearance) integer codes of cell i.  Outputs: counts[s*K+k];
+ * first_ct[k] / first_smp[s] = smallest cell index carrying that code
+ * (n_cells if absent) so the host can restore `.unique()` order.
+ */
+int pilot_hist(const int32_t *ct_code, const int32_t *smp_code, int64_t n_cells,
+               int K, int S, int64_t *counts, int64_t *first_ct,
+               int64_t *first_smp, void *stream);
+
+/*
+ * Dirichlet-smoothed proportions, Trajectory.py:405-409 and :428-430, FP64,
+ * bit-exact with the reference (sequential sums, no FMA contraction).
+ * counts_raw is pilot_hist's table (S_raw x K_raw, raw-code order); perm_s[S] /
+ * perm_k[K] (device int32, NULL = identity) list the raw codes in order of first
+ * appearance, so props[s*K+k] and counts_out[s*K+k] (optional) come out in the
+ * reference's `.unique()` order.  normalization==0 copies the raw counts
+ * (Trajectory.py:425).
+ */
+int pilot_props_finalize(const int64_t *counts_raw, int K_raw, int S_raw,
+                         const int32_t *perm_k, const int32_t *perm_s, int K,
+                         int S, int64_t n_cells, double regulizer,
+                         int normalization, double *props, int64_t *counts_out,
+                         void *stream);
+
+/*
+ * (2a) Per-type, per-dimension MEDIAN of the embedding rows in the input dtype
+ * (NaNs ignored, even counts -> (lo+hi)/2 rounded in the input dtype) --
+ * replaces data[mask].median(axis=0), Trajectory.py:465-466.
+ * X is row-major n_cells x D with leading dimension ldx (elements).
+ * centroids (K*D, dtype of X) and centroids_f64 (K*D) are both written.
+ */
+int pilot_centroid_median(const void *X, int dtype, int64_t n_cells, int D,
+                          int64_t ldx, const int32_t *ct_code, int K,
+                          void *centroids, double *centroids_f64,
+                          void *workspace, size_t workspace_bytes, void *stream);
+
+/*
+ * (2b) K x K distance matrix between centroids -- replaces
+ * squareform(pdist(centroids, metric)), Trajectory.py:468-469.  Also writes
+ * cost_norm = cost / max(cost) (Trajectory.py:101) and *cost_max.
+ */
+int pilot_cdist(const double *centroids_f64, int K, int D, int metric,
+                double *cost, double *cost_norm, double *cost_max, void *stream);
+
+/*
+ * (3) All-pairs stabilised Sinkhorn -- replaces the loop over
+ * ot.sinkhorn2(a_i, a_j, cost, reg, method="sinkhorn_stabilized"),
+ * Trajectory.py:513-515 (POT defaults: num_iter_max=1000, stop_thr=1e-9,
+ * tau=1e3, check_every=20).  out[l] = sum(M * Gamma) of local problem l.
+ * iters / absorptions / status may be NULL.
+ * algo: 0 = batched shared-Gibbs-kernel solver (fast path; problems it cannot
+ *           represent are re-solved by the reference-form kernel),
+ *       1 = reference-form kernel only (per-problem Gibbs kernel, literal schedule).
+ */
+int pilot_sinkhorn_pairs(const double *props, int S, int K, const double *cost,
+                         double reg, int num_iter_max, double stop_thr,
+                         double tau, int check_every,
+                         const pilot_pair_range *range, int algo, double *out,
+                         int32_t *iters, int32_t *absorptions, int32_t *status,
+                         void *workspace, size_t workspace_bytes, void *stream);
+
+/*
+ * (4) All-pairs exact EMD -- replaces the loop over ot.emd2(a_i, a_j, cost),
+ * Trajectory.py:507-511 (b is rescaled to a's mass as emd2 does).
+ * out[l] = optimal transport cost of local problem l; status/pivots may be NULL.
+ */
+int pilot_emd_pairs(const double *props, int S, int K, const double *cost,
+                    int64_t max_pivots, const pilot_pair_range *range,
+                    double *out, int32_t *status, int32_t *pivots,
+                    void *workspace, size_t workspace_bytes, void *stream);
+
+/*
+ * (5) Packed per-rank results (as laid out by an all-gather: rank r's chunk at
+ * packed + r*chunk_stride) -> dense S x S row-major matrix, EMD[i,j] with
+ * i = row sample (a), j = column sample (b) as Trajectory.py:511/515.
+ * UPPER mode mirrors into the lower triangle and writes `diag_value` on the
+ * diagonal.
+ */
+int pilot_unpack_pairs(const double *packed, int64_t chunk_stride, int S,
+                       const pilot_pair_range *range, double diag_value,
+                       double *dense, void *stream);
+
+/*
+ * Pipe-peak microbenchmarks used as roofline denominators:
+ * kind 0 = FP64 FMA, 1 = FP32 FMA, 2 = FP64 mma.sync (DMMA m8n8k4).
+ * Runs on `stream`, returns achieved TFLOP/s in *h_tflops (host pointer).
+ */
+int pilot_pipe_peak(int kind, double *h_tflops, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PILOT_B200_H */

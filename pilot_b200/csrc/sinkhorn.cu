@@ -1,0 +1,67 @@
+// C-ABI entry of kernel (3): dispatch between the batched shared-Gibbs-kernel solver and
+// the reference-form kernel (reference call site: pilotpy/tools/Trajectory.py:513-515).
+#include "sinkhorn.cuh"
+
+namespace pilot {
+
+struct SkWs {
+    unsigned long long *counter_fast, *n_redo, *counter_slow;
+    double *setup, *scratch;
+    long long *redo;
+};
+
+static size_t sk_ws_bytes(int K)
+{
+    const int KP = skb_pad(K <= 64 ? K : 64);
+    return 256 + skb_setup_bytes(KP) + skb_scratch_bytes(KP, sm_count()) + (size_t)SK_REDO_CAP * sizeof(long long);
+}
+
+size_t sinkhorn_ws_bytes(int K) { return sk_ws_bytes(K); }
+
+}  // namespace pilot
+
+extern "C" int pilot_sinkhorn_pairs(const double *props, int S, int K, const double *cost, double reg,
+                                    int num_iter_max, double stop_thr, double tau, int check_every,
+                                    const pilot_pair_range *range, int algo, double *out, int32_t *iters,
+                                    int32_t *absorptions, int32_t *status, void *workspace,
+                                    size_t workspace_bytes, void *stream)
+{
+    using namespace pilot;
+    PILOT_CHECK_ARG(props && cost && out && workspace, "pilot_sinkhorn_pairs: NULL pointer");
+    PILOT_CHECK_ARG(S >= 1 && K >= 1, "pilot_sinkhorn_pairs: S=%d K=%d", S, K);
+    PILOT_CHECK_ARG(reg > 0.0, "pilot_sinkhorn_pairs: reg must be > 0");
+    PILOT_CHECK_ARG(num_iter_max >= 1 && check_every >= 1, "pilot_sinkhorn_pairs: bad iteration parameters");
+    PILOT_CHECK_ARG(algo == 0 || algo == 1, "pilot_sinkhorn_pairs: algo %d", algo);
+    PILOT_CHECK_ARG(sinkhorn_ref_smem(K) <= 200 * 1024, "pilot_sinkhorn_pairs: K=%d too large (max ~150)", K);
+    PILOT_CHECK_ARG(workspace_bytes >= sk_ws_bytes(K), "pilot_sinkhorn_pairs: workspace %zu < %zu bytes",
+                    workspace_bytes, sk_ws_bytes(K));
+    PairMap pm;
+    int rc = make_pair_map(range, S, &pm);
+    if (rc) return rc;
+    if (pm.n_local == 0) return 0;
+    cudaStream_t st = (cudaStream_t)stream;
+    SkParams prm{reg, stop_thr, tau, num_iter_max, check_every};
+    unsigned char *p = (unsigned char *)workspace;
+    SkWs ws;
+    ws.counter_fast = (unsigned long long *)p;
+    ws.n_redo = ws.counter_fast + 1;
+    ws.counter_slow = ws.counter_fast + 2;
+    PILOT_CUDA(cudaMemsetAsync(p, 0, 256, st));
+    if (algo == 1 || K > 64)
+        return sinkhorn_ref_launch(props, K, cost, prm, pm, nullptr, nullptr, 0, out, iters, absorptions, status,
+                                   ws.counter_slow, st);
+    const int KP = skb_pad(K);
+    ws.setup = (double *)(p + 256);
+    ws.scratch = (double *)(p + 256 + skb_setup_bytes(KP));
+    ws.redo = (long long *)(p + 256 + skb_setup_bytes(KP) + skb_scratch_bytes(KP, sm_count()));
+    // persistent grid: one CTA per SM, fewer when there is less than one slot-load of work
+    const int slots_per_cta = 8 * (32 / (KP / 8)) * 4;
+    long long ctas = (pm.n_local + slots_per_cta - 1) / slots_per_cta;
+    if (ctas > sm_count()) ctas = sm_count();
+    rc = skb_launch(props, K, cost, prm, pm, ws.setup, ws.scratch, (int)ctas, out, iters, absorptions, status,
+                    ws.counter_fast, ws.redo, ws.n_redo, st);
+    if (rc) return rc;
+    // problems the scaled form could not represent (normally none): reference-form kernel
+    return sinkhorn_ref_launch(props, K, cost, prm, pm, ws.redo, ws.n_redo, SK_REDO_CAP, out, iters, absorptions,
+                               status, ws.counter_slow, st);
+}

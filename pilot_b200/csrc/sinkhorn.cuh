@@ -1,0 +1,28 @@
+// Shared declarations of the two Sinkhorn kernels (sinkhorn_ref.cu, sinkhorn_batched.cu).
+#pragma once
+#include "common.cuh"
+
+namespace pilot {
+
+struct SkParams {
+    double reg, stop_thr, tau;
+    int num_iter_max, check_every;
+};
+
+constexpr long long SK_REDO_CAP = 1LL << 20;
+
+size_t sinkhorn_ref_smem(int K);
+int sinkhorn_ref_launch(const double *props, int K, const double *cost, const SkParams &prm, const PairMap &pm,
+                        const long long *list, const unsigned long long *n_list_dev, long long max_list,
+                        double *out, int *iters, int *absorptions, int *status, unsigned long long *counter,
+                        cudaStream_t st);
+
+int skb_pad(int K);
+size_t skb_setup_bytes(int KP);
+size_t skb_smem_bytes(int KP);
+size_t skb_scratch_bytes(int KP, int ctas);
+int skb_launch(const double *props, int K, const double *cost, const SkParams &prm, const PairMap &pm,
+               double *setup, double *scratch, int ctas, double *out, int *iters, int *absn, int *status,
+               unsigned long long *counter, long long *redo, unsigned long long *n_redo, cudaStream_t st);
+
+}  // namespace pilot

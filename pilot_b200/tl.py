@@ -1,0 +1,301 @@
+"""Host-side mirror of the reference's patient-distance interface.
+
+Same names, argument meaning, return containers and error behaviour as
+``/root/reference/pilotpy/tools/Trajectory.py`` (``wasserstein_distance`` :36-116,
+``set_path_for_results`` :146-164, ``extract_data_anno_*`` :234-299,
+``Cluster_Representations`` :377-436, ``cost_matrix`` :441-475,
+``wasserstein_d`` :479-523, ``return_real_labels`` :617-642) so that a PILOT
+user can switch ``pl.tl.wasserstein_distance`` for this one and everything
+downstream (trajectory, clustering, statistics) runs unchanged.
+
+The arithmetic of the four stages runs in hand-written sm_100a CUDA kernels
+behind the C ABI (``include/pilot_b200.h``); this module only factorises
+labels, moves buffers and assembles the pandas/NumPy containers of the
+``adata.uns`` contract.  There is no CPU fallback.
+"""
+from __future__ import annotations
+
+import os
+import warnings
+from typing import Dict, List, Optional, Tuple
+
+import numpy as np
+import pandas as pd
+import torch
+
+from . import ops, pairs
+
+warnings.filterwarnings("ignore")  # the reference silences everything at import (Trajectory.py:32)
+
+path_to_results = None  # module global read by pilotpy's cell_importance (Trajectory.py:708)
+
+
+# ---------------------------------------------------------------------------
+# extraction (host-only; Trajectory.py:146-164, 234-299)
+# ---------------------------------------------------------------------------
+def set_path_for_results():
+    """Create ./Results_PILOT/plots like the reference and return the path."""
+    if not os.path.exists("Results_PILOT/plots"):
+        os.makedirs("Results_PILOT/plots")
+    return "Results_PILOT/plots"
+
+
+def extract_data_anno_scRNA_from_h5ad(adata, emb_matrix="PCA", clusters_col="cell_type", sample_col="sampleID",
+                                      status="status"):
+    """(data, annot) DataFrames from adata.obsm[emb_matrix] and three obs columns."""
+    global path_to_results
+    data = adata.obsm[emb_matrix]
+    cols = ["PCA_" + str(i) for i in range(1, adata.obsm[emb_matrix].shape[1] + 1)]
+    data = pd.DataFrame(data, columns=cols)
+    data = data.reset_index(drop=True)
+    annot = adata.obs[[clusters_col, sample_col, status]]
+    annot.columns = ["cell_type", "sampleID", "status"]
+    annot = annot.reset_index(drop=True)
+    path_to_results = set_path_for_results()
+    return data, annot
+
+
+def extract_data_anno_pathomics_from_h5ad(adata, var_names=[], clusters_col="Cell_type", sample_col="sampleID",
+                                          status="status"):
+    """(data, annot) DataFrames from adata[:, var_names].X and three obs columns."""
+    global path_to_results
+    data = adata[:, var_names].X
+    data = pd.DataFrame(data, columns=var_names)
+    data = data.reset_index(drop=True)
+    annot = adata.obs[[clusters_col, sample_col, status]]
+    annot.columns = ["cell_type", "sampleID", "status"]
+    annot = annot.reset_index(drop=True)
+    path_to_results = set_path_for_results()
+    return data, annot
+
+
+# ---------------------------------------------------------------------------
+# host factorisation helpers
+# ---------------------------------------------------------------------------
+def _raw_codes(col: pd.Series) -> Tuple[np.ndarray, object]:
+    """Integer codes of a label column without hashing when it is Categorical.
+    Returns (int32 codes, labels-by-code).  Missing labels are an error."""
+    if isinstance(col.dtype, pd.CategoricalDtype):
+        codes = col.cat.codes.to_numpy()
+        labels = col.cat.categories
+    else:
+        codes, labels = pd.factorize(col, sort=False)
+    if len(codes) and codes.min() < 0:
+        raise ValueError(f"column {col.name!r} contains missing labels")
+    return np.ascontiguousarray(codes, dtype=np.int32), labels
+
+
+def _unique_in_order(col: pd.Series, labels, perm: np.ndarray):
+    """What ``col.unique()`` returns (same container type), built from the codes."""
+    if isinstance(col.dtype, pd.CategoricalDtype):
+        return pd.Categorical.from_codes(perm, dtype=col.dtype)
+    if isinstance(labels, pd.Index):
+        taken = labels.take(perm)
+        # extension dtypes (pandas >= 3 `str`) come back from .unique() as their ExtensionArray
+        return taken.array if isinstance(taken.dtype, pd.api.extensions.ExtensionDtype) else taken.to_numpy()
+    return np.asarray(labels)[perm]
+
+
+def _device() -> torch.device:
+    if not torch.cuda.is_available():
+        raise ops._lib.PilotLibraryError("pilot_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
+    return torch.device("cuda", torch.cuda.current_device())
+
+
+def _to_device(arr: np.ndarray) -> torch.Tensor:
+    return torch.from_numpy(arr).to(_device(), non_blocking=False)
+
+
+class _Labels:
+    """Device-resident factorised annotation shared by the stages of one call."""
+
+    def __init__(self, annot: pd.DataFrame, cell_col_name, sample_col_name):
+        self.n = len(annot)
+        self.cell_col = annot[cell_col_name]
+        self.samp_col = annot[sample_col_name]
+        ct, self.ct_labels = _raw_codes(self.cell_col)
+        sm, self.sm_labels = _raw_codes(self.samp_col)
+        self.K_raw, self.S_raw = len(self.ct_labels), len(self.sm_labels)
+        self.ct_dev = _to_device(ct)
+        self.sm_dev = _to_device(sm)
+        self.counts_raw, first_ct, first_smp = ops.hist(self.ct_dev, self.sm_dev, self.K_raw, self.S_raw)
+        first = torch.cat([first_ct, first_smp]).cpu().numpy()  # the only sync of stage 1
+        fk, fs = first[: self.K_raw], first[self.K_raw:]
+        pk = np.argsort(fk, kind="stable")
+        ps = np.argsort(fs, kind="stable")
+        self.perm_k = np.ascontiguousarray(pk[fk[pk] < self.n], dtype=np.int32)  # raw codes in .unique() order
+        self.perm_s = np.ascontiguousarray(ps[fs[ps] < self.n], dtype=np.int32)
+        self.first_smp = fs[self.perm_s]
+        self.perm_k_dev = _to_device(self.perm_k)
+        self.perm_s_dev = _to_device(self.perm_s)
+        self.K, self.S = len(self.perm_k), len(self.perm_s)
+        self.cells = _unique_in_order(self.cell_col, self.ct_labels, self.perm_k)
+        self.samples = _unique_in_order(self.samp_col, self.sm_labels, self.perm_s)
+
+    def proportions(self, regulizer, normalization) -> Tuple[torch.Tensor, torch.Tensor]:
+        return ops.props_finalize(self.counts_raw, self.perm_k_dev, self.perm_s_dev, self.n, regulizer,
+                                  bool(normalization == True))  # noqa: E712  (reference: `normalization == True`)
+
+
+def _embedding_to_device(data) -> torch.Tensor:
+    X = data.to_numpy() if isinstance(data, pd.DataFrame) else np.asarray(data)
+    if X.dtype not in (np.float32, np.float64):
+        X = X.astype(np.float64)  # pandas' nanmedian promotes non-float input to float64
+    return _to_device(np.ascontiguousarray(X))
+
+
+def _props_dict(samples, props_host: np.ndarray) -> Dict[object, np.ndarray]:
+    return {s: props_host[i].copy() for i, s in enumerate(samples)}
+
+
+def _cost_frame(dis: np.ndarray, cells) -> pd.DataFrame:
+    # the reference's own three statements (Trajectory.py:470-473) so index types match on any pandas
+    cost = pd.DataFrame.from_dict(dis).T
+    cost.columns = cells
+    cost["cell_types"] = cells
+    cost = cost.set_index("cell_types")
+    return cost
+
+
+def _emd_frame(EMD: np.ndarray, samples_id: List) -> pd.DataFrame:
+    # DataFrame.from_dict(EMD).T (Trajectory.py:518) is the transpose; build it without the S x S copies
+    emd = pd.DataFrame(EMD.T, columns=samples_id)
+    emd["sampleID"] = samples_id
+    emd = emd.set_index("sampleID")
+    return emd
+
+
+# ---------------------------------------------------------------------------
+# Stage 1: proportions (Trajectory.py:377-436)
+# ---------------------------------------------------------------------------
+def Cluster_Representations(df, cell_col=0, sample_col=1, regulizer=0.2, normalization=True):
+    """Per-sample, Dirichlet-smoothed cell-type proportions.
+
+    Returns ``{sample: float64[K]}`` with samples and cell types in order of first
+    appearance.  Like the reference, the frame must carry the columns
+    ``'cell_type'`` and ``'sampleID'`` (hard-coded at Trajectory.py:405,407,429).
+    """
+    cell_name = df.columns[cell_col]
+    samp_name = df.columns[sample_col]
+    if "cell_type" not in df.columns:
+        raise KeyError("cell_type")
+    if normalization == True and "sampleID" not in df.columns:  # noqa: E712
+        raise KeyError("sampleID")
+    if cell_name != "cell_type" or (normalization == True and samp_name != "sampleID"):  # noqa: E712
+        raise ValueError("Cluster_Representations: cell_col/sample_col must select the 'cell_type'/'sampleID' "
+                         "columns (the reference hard-codes these names, Trajectory.py:405-429)")
+    lab = _Labels(df, cell_name, samp_name)
+    props, counts = lab.proportions(regulizer, normalization)
+    counts_h = counts.cpu().numpy()
+    if int(counts_h.sum()) != lab.n:
+        raise ValueError("label codes out of range")
+    return _props_dict(lab.samples, props.cpu().numpy())
+
+
+# ---------------------------------------------------------------------------
+# Stage 2: cost matrix (Trajectory.py:441-475)
+# ---------------------------------------------------------------------------
+def _cost_device(lab: _Labels, X_dev: torch.Tensor, metric) -> Tuple[torch.Tensor, torch.Tensor]:
+    if X_dev.shape[0] != lab.n:
+        raise ValueError(f"Item wrong length {lab.n} instead of {X_dev.shape[0]}.")
+    _, cent64_raw = ops.centroid_median(X_dev, lab.ct_dev, lab.K_raw)
+    cent64 = cent64_raw.index_select(0, lab.perm_k_dev.long()).contiguous()
+    cost, cost_norm, _ = ops.cdist(cent64, metric)
+    return cost, cost_norm
+
+
+def cost_matrix(annot, data, metric="cosine"):
+    """Median centroid of every cell type, then their pairwise distances.
+
+    Returns ``(dis, cost)``: the K x K ndarray and the labelled DataFrame
+    (index name ``'cell_types'``), both un-normalised.
+    """
+    lab = _Labels(annot, annot.columns[0], annot.columns[1] if annot.shape[1] > 1 else annot.columns[0])
+    cost, _ = _cost_device(lab, _embedding_to_device(data), metric)
+    dis = cost.cpu().numpy()
+    return dis, _cost_frame(dis, lab.cells)
+
+
+# ---------------------------------------------------------------------------
+# Stage 3: all-pairs OT (Trajectory.py:479-523)
+# ---------------------------------------------------------------------------
+def _check_emd_inputs(P: np.ndarray, cost: np.ndarray) -> None:
+    # what ot.emd2 asserts per pair (POT ot/lp/__init__.py::emd2)
+    assert P.shape[1] == cost.shape[0] and P.shape[1] == cost.shape[1], \
+        "Dimension mismatch, check dimensions of M with a and b"
+    sums = P.sum(axis=1)
+    if sums.size and float(sums.max() - sums.min()) >= 1.5e-6:
+        raise AssertionError("\nArrays are not almost equal to 6 decimals\n"
+                             "a and b vector must have the same sum")
+
+
+def wasserstein_d(Clu_rep, cost, regularized="unreg", reg=0.1):
+    """All ordered sample pairs: exact EMD (``regularized == "unreg"``) or stabilised
+    Sinkhorn (anything else).  Returns ``(EMD ndarray [S,S], DataFrame indexed by sampleID)``."""
+    samples_id = list(Clu_rep.keys())
+    P = np.ascontiguousarray(np.stack([np.asarray(Clu_rep[s], dtype=np.float64) for s in samples_id])) \
+        if samples_id else np.zeros((0, 0))
+    C = np.ascontiguousarray(np.asarray(cost, dtype=np.float64))
+    if len(samples_id) == 0:
+        EMD = np.zeros((0, 0))
+        return EMD, _emd_frame(EMD, samples_id)
+    if regularized == "unreg":
+        _check_emd_inputs(P, C)
+    EMD = pairs.all_pairs(_to_device(P), _to_device(C), regularized, reg).cpu().numpy()
+    return EMD, _emd_frame(EMD, samples_id)
+
+
+# ---------------------------------------------------------------------------
+# labels (Trajectory.py:617-642)
+# ---------------------------------------------------------------------------
+def return_real_labels(df, category="status", sample_col=1):
+    """First ``category`` value of every sample, samples in order of first appearance."""
+    scol = df.columns[sample_col]
+    first = ~df[scol].duplicated(keep="first")
+    return list(df[category][first])
+
+
+# ---------------------------------------------------------------------------
+# entry point (Trajectory.py:36-116)
+# ---------------------------------------------------------------------------
+def wasserstein_distance(adata, emb_matrix="X_PCA", clusters_col="cell_types", sample_col="sampleID",
+                         status="status", metric="cosine", regulizer=0.2, normalization=True,
+                         regularized="unreg", reg=0.1, res=0.01, steper=0.01, data_type="scRNA",
+                         return_sil_ari=False):
+    """Drop-in for ``pilotpy.tl.wasserstein_distance``: writes ``data``, ``annot``,
+    ``proportions``, ``cost``, ``EMD_df``, ``EMD`` and ``real_labels`` into ``adata.uns``."""
+    if data_type == "scRNA":
+        data, annot = extract_data_anno_scRNA_from_h5ad(adata, emb_matrix=emb_matrix, clusters_col=clusters_col,
+                                                        sample_col=sample_col, status=status)
+    else:
+        data, annot = extract_data_anno_pathomics_from_h5ad(adata, var_names=list(adata.var_names),
+                                                            clusters_col=clusters_col, sample_col=sample_col,
+                                                            status=status)
+    adata.uns["data"] = data
+    adata.uns["annot"] = annot
+
+    lab = _Labels(annot, "cell_type", "sampleID")
+    X_dev = _embedding_to_device(data)
+    props, counts = lab.proportions(regulizer, normalization)
+    cost, cost_norm = _cost_device(lab, X_dev, metric)
+    props_h = props.cpu().numpy()
+    if int(counts.sum().item()) != lab.n:
+        raise ValueError("label codes out of range")
+    if regularized == "unreg":
+        _check_emd_inputs(props_h, np.empty((lab.K, lab.K)))
+    emd_dev = pairs.all_pairs(props, cost_norm, regularized, reg)
+
+    adata.uns["proportions"] = _props_dict(lab.samples, props_h)
+    dis = cost.cpu().numpy()
+    adata.uns["cost"] = _cost_frame(dis, lab.cells)
+    EMD = emd_dev.cpu().numpy()
+    adata.uns["EMD_df"] = _emd_frame(EMD, list(adata.uns["proportions"].keys()))
+    adata.uns["EMD"] = EMD
+
+    if return_sil_ari:
+        raise NotImplementedError(
+            "return_sil_ari=True runs the reference's Leiden/ARI/silhouette tail (Trajectory.py:107-113, "
+            "scanpy + leidenalg), which is outside the patient-distance hot path (SURVEY.md 8f #4); call "
+            "pilotpy.tl.Clustering / Sil_computing on adata.uns['EMD'] instead.")
+    # first status per sample, via the first-appearance cell index the histogram kernel produced
+    adata.uns["real_labels"] = list(annot["status"].to_numpy()[lab.first_smp])

@@ -1,0 +1,83 @@
+"""End-to-end drop-in parity of pilot_b200.tl.wasserstein_distance on a duck-typed AnnData:
+the committed golden fixtures (reference outputs) and the oracle on BASELINE config C1."""
+import numpy as np
+import pandas as pd
+import pytest
+
+from conftest import build_golden_adata, golden_kwargs, golden_names, load_golden
+from oracle import pilot_oracle as po
+from pilot_b200 import synth, tl
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("name", golden_names())
+def test_golden_fixture(name):
+    g = load_golden(name)
+    kw = golden_kwargs(g["case"])
+    adata = build_golden_adata(g["case"])
+    tl.wasserstein_distance(adata, **kw)
+    u = adata.uns
+    assert set(u) >= {"data", "annot", "proportions", "cost", "EMD_df", "EMD", "real_labels"}
+    assert isinstance(u["proportions"], dict)
+    assert [str(k) for k in u["proportions"].keys()] == list(g["samples"])
+    P = np.stack(list(u["proportions"].values()))
+    assert np.array_equal(P, g["props"]), "proportions must be bit-exact"
+    assert [str(c) for c in u["cost"].columns] == list(g["cells"])
+    assert u["cost"].index.name == "cell_types"
+    np.testing.assert_allclose(u["cost"].to_numpy(), g["cost"], rtol=1e-12, atol=1e-15)
+    assert isinstance(u["EMD"], np.ndarray) and u["EMD"].dtype == np.float64 and u["EMD"].flags.c_contiguous
+    np.testing.assert_allclose(u["EMD"], g["EMD"], rtol=1e-9, atol=1e-14)
+    assert u["EMD_df"].index.name == "sampleID"
+    np.testing.assert_allclose(u["EMD_df"].to_numpy(), g["EMD_df"], rtol=1e-9, atol=1e-14)
+    assert [str(x) for x in u["real_labels"]] == list(g["real_labels"])
+    assert list(u["annot"].columns) == ["cell_type", "sampleID", "status"]
+    assert len(u["data"]) == len(u["annot"])
+
+
+@pytest.mark.parametrize("labels", ["str", "categorical"])
+def test_config_c1_full(labels):
+    """BASELINE configs[0]: 200K cells, 30-dim, 10 types, 20 samples, cosine, exact EMD."""
+    adata = synth.make_adata("c1", labels=labels)
+    tl.wasserstein_distance(adata, emb_matrix="X_PCA", clusters_col="cell_types", sample_col="sampleID",
+                            status="status")
+    annot, data = adata.uns["annot"], adata.uns["data"]
+    wprops = po.cluster_representations(annot)
+    assert list(wprops.keys()) == list(adata.uns["proportions"].keys())
+    for k in wprops:
+        assert np.array_equal(wprops[k], adata.uns["proportions"][k])
+    wdis, wcost = po.cost_matrix(annot, data, "cosine")
+    np.testing.assert_allclose(adata.uns["cost"].to_numpy(), wdis, rtol=1e-12, atol=1e-15)
+    pd.testing.assert_index_equal(adata.uns["cost"].index, wcost.index)
+    wEMD, wdf = po.wasserstein_d(wprops, wdis / wdis.max())
+    np.testing.assert_allclose(adata.uns["EMD"], wEMD, rtol=1e-9, atol=1e-15)
+    pd.testing.assert_index_equal(adata.uns["EMD_df"].index, wdf.index)
+    assert adata.uns["real_labels"] == po.return_real_labels(annot)
+
+
+def test_sinkhorn_e2e_and_regularized_string_semantics():
+    adata = synth.make_adata("c1", scale=0.1)
+    # anything but the string "unreg" selects Sinkhorn (Trajectory.py:507)
+    tl.wasserstein_distance(adata, regularized=True, reg=0.1)
+    annot, data = adata.uns["annot"], adata.uns["data"]
+    props = po.cluster_representations(annot)
+    dis, _ = po.cost_matrix(annot, data, "cosine")
+    want, wdf = po.wasserstein_d(props, dis / dis.max(), regularized="reg", reg=0.1)
+    np.testing.assert_allclose(adata.uns["EMD"], want, rtol=1e-9)
+    np.testing.assert_allclose(adata.uns["EMD_df"].to_numpy(), want.T, rtol=1e-9)
+    assert np.abs(np.diag(adata.uns["EMD"])).min() > 0
+
+
+def test_unnormalised_counts_raise_like_pot():
+    adata = synth.make_adata("c1", scale=0.05)
+    with pytest.raises(AssertionError):
+        tl.wasserstein_distance(adata, normalization=False)
+
+
+def test_wasserstein_d_public_function():
+    P, M = synth.make_pairs(15, 10, seed=8)
+    rep = {f"s{i}": P[i] for i in range(15)}
+    EMD, df = tl.wasserstein_d(rep, M)
+    want, wdf = po.wasserstein_d(rep, M)
+    np.testing.assert_allclose(EMD, want, rtol=1e-9, atol=1e-15)
+    pd.testing.assert_frame_equal(df, wdf, rtol=1e-9, atol=1e-15)

@@ -1,0 +1,140 @@
+"""GPU parity of stage 3 (all-pairs exact EMD and stabilised Sinkhorn) against the oracle, the
+packed/partitioned layout, and size-independent properties at larger sizes."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import pilot_oracle as po
+from pilot_b200 import _lib, ops, pairs, synth
+
+pytestmark = pytest.mark.gpu
+
+EMD_RTOL = 1e-9      # BASELINE.json: 1e-9 relative in FP64 mode
+SK_RTOL = 1e-9
+
+
+def dev(x):
+    return torch.from_numpy(np.ascontiguousarray(x)).cuda()
+
+
+def oracle_emd_matrix(P, M):
+    return po.emd_rows(P, M, 0, P.shape[0])
+
+
+@pytest.mark.parametrize("K", [1, 2, 3, 10, 30, 32, 33, 40, 64])
+def test_emd_pairs_match_oracle(K):
+    S = 24
+    P, M = synth.make_pairs(S, K, seed=300 + K)
+    if K == 1:
+        M = np.zeros((1, 1))
+    rng = ops.make_range(S * S, _lib.PAIRS_FULL)
+    out, status, piv = ops.emd_pairs(dev(P), dev(M), rng, want_info=True)
+    got = out.cpu().numpy().reshape(S, S)
+    want = oracle_emd_matrix(P, M)
+    assert (status.cpu().numpy() == 0).all()
+    np.testing.assert_allclose(got, want, rtol=EMD_RTOL, atol=1e-15)
+    assert np.abs(np.diag(got)).max() <= 1e-15
+
+
+def test_emd_degenerate_inputs():
+    K = 12
+    P, M = synth.make_pairs(6, K, seed=1)
+    P[1] = P[0]                                   # identical samples
+    P[2] = np.roll(P[0], 1)                       # permuted masses
+    P[3, :4] = 0.0; P[3] /= P[3].sum()            # zero masses (POT drops them)
+    P[4] = 1.0 / K                                # uniform
+    P[5] = P[4]
+    rng = ops.make_range(36, _lib.PAIRS_FULL)
+    out, status, _ = ops.emd_pairs(dev(P), dev(M), rng, want_info=True)
+    got = out.cpu().numpy().reshape(6, 6)
+    want = oracle_emd_matrix(P, M)
+    assert (status.cpu().numpy() == 0).all()
+    np.testing.assert_allclose(got, want, rtol=EMD_RTOL, atol=1e-14)
+
+
+def test_emd_nonmetric_cost_and_counts():
+    # raw counts with equal totals (normalization=False) and an asymmetric, non-zero-diagonal cost
+    rng_ = np.random.default_rng(3)
+    K, S = 9, 10
+    P = rng_.multinomial(500, np.ones(K) / K, size=S).astype(np.float64)
+    M = rng_.random((K, K)) + 0.1
+    got = pairs.all_pairs(dev(P), dev(M), "unreg").cpu().numpy()
+    want = oracle_emd_matrix(P, M)
+    np.testing.assert_allclose(got, want, rtol=EMD_RTOL, atol=1e-12)
+
+
+@pytest.mark.parametrize("K,reg", [(10, 0.1), (30, 0.1), (64, 0.1), (64, 0.01), (40, 0.02), (5, 0.5)])
+@pytest.mark.parametrize("algo", [0, 1])
+def test_sinkhorn_pairs_match_oracle(K, reg, algo):
+    S = 12 if reg < 0.05 else 20
+    P, M = synth.make_pairs(S, K, seed=400 + K)
+    rng = ops.make_range(S * S, _lib.PAIRS_FULL)
+    out, iters, absn, status = ops.sinkhorn_pairs(dev(P), dev(M), reg, rng, algo=algo, want_info=True)
+    want, witers, wabs = po.sinkhorn_rows(P, M, reg, 0, S)
+    got = out.cpu().numpy().reshape(S, S)
+    np.testing.assert_array_equal(iters.cpu().numpy().reshape(S, S), witers)
+    np.testing.assert_array_equal(absn.cpu().numpy().reshape(S, S), wabs)
+    np.testing.assert_allclose(got, want, rtol=SK_RTOL, atol=1e-300)
+    st = status.cpu().numpy()
+    assert ((st == 0) | (st == 1)).all()
+
+
+def test_sinkhorn_zero_mass_goes_through_reference_form():
+    # zero masses make POT's log(u) = -inf -> NaN roll-back; the batched kernel must hand these over
+    K, S = 10, 4
+    P, M = synth.make_pairs(S, K, seed=2)
+    P[1, 3] = 0.0
+    P[1] /= P[1].sum()
+    rng = ops.make_range(S * S, _lib.PAIRS_FULL)
+    a = ops.sinkhorn_pairs(dev(P), dev(M), 0.01, rng, algo=0).cpu().numpy()
+    b = ops.sinkhorn_pairs(dev(P), dev(M), 0.01, rng, algo=1).cpu().numpy()
+    want, _, _ = po.sinkhorn_rows(P, M, 0.01, 0, S)
+    np.testing.assert_allclose(b, want.ravel(), rtol=1e-9, equal_nan=True)
+    np.testing.assert_allclose(a, want.ravel(), rtol=1e-9, equal_nan=True)
+
+
+@pytest.mark.parametrize("mode", [_lib.PAIRS_FULL, _lib.PAIRS_UPPER])
+@pytest.mark.parametrize("nranks,block", [(1, None), (2, 7), (4, 5), (8, 64)])
+def test_partition_invariance_and_unpack(mode, nranks, block):
+    S, K = 23, 10
+    P, M = synth.make_pairs(S, K, seed=11)
+    Pd, Md = dev(P), dev(M)
+    total = ops.n_pairs(S, mode)
+    ref = pairs.all_pairs(Pd, Md, "unreg", symmetric=(mode == _lib.PAIRS_UPPER)).cpu().numpy()
+    block = block or total
+    chunk = max(1, pairs.range_count(total, block, nranks, 0))
+    packed = torch.zeros((nranks * chunk,), dtype=torch.float64, device="cuda")
+    for r in range(nranks):
+        rng = _lib.PairRange(total=total, block=block, nranks=nranks, rank=r, mode=mode, reserved=0)
+        n = _lib.range_count(rng)
+        if n:
+            ops.emd_pairs(Pd, Md, rng, out=packed[r * chunk:(r + 1) * chunk])
+    rng0 = _lib.PairRange(total=total, block=block, nranks=nranks, rank=0, mode=mode, reserved=0)
+    dense = ops.unpack_pairs(packed, chunk, S, rng0, 0.0).cpu().numpy()
+    assert np.array_equal(dense, ref), "partitioned result must be bit-identical"
+    want = oracle_emd_matrix(P, M)
+    np.testing.assert_allclose(dense, want, rtol=EMD_RTOL, atol=1e-15)
+
+
+def test_properties_at_scale():
+    """Size-independent properties on a C5-shaped slice (K = 64): symmetry and zero diagonal of the
+    exact EMD computed as ORDERED pairs, EMD <= Sinkhorn cost, determinism, Sinkhorn row marginal."""
+    S, K = 160, 64
+    P, M = synth.make_pairs(S, K, seed=5)
+    Pd, Md = dev(P), dev(M)
+    full = ops.emd_pairs(Pd, Md, ops.make_range(S * S, _lib.PAIRS_FULL)).cpu().numpy().reshape(S, S)
+    assert np.abs(full - full.T).max() <= 1e-12
+    assert np.abs(np.diag(full)).max() <= 1e-15
+    tri = pairs.all_pairs(Pd, Md, "unreg").cpu().numpy()
+    np.testing.assert_allclose(tri, full, rtol=1e-10, atol=1e-15)
+    sk1 = pairs.all_pairs(Pd, Md, "reg", 0.1).cpu().numpy()
+    sk2 = pairs.all_pairs(Pd, Md, "reg", 0.1).cpu().numpy()
+    assert np.array_equal(sk1, sk2), "two runs must be bit-identical"
+    off = ~np.eye(S, dtype=bool)
+    assert (sk1[off] >= full[off] * (1 - 1e-9)).all()
+    # spot-check 64 random entries against the oracle
+    r = np.random.default_rng(0)
+    for i, j in zip(r.integers(0, S, 64), r.integers(0, S, 64)):
+        assert abs(tri[i, j] - po.emd2(P[i], P[j], M)) <= EMD_RTOL * max(tri[i, j], 1e-12)
+        w = po.sinkhorn2(P[i], P[j], M, 0.1)
+        assert abs(sk1[i, j] - w) <= SK_RTOL * w

@@ -1,0 +1,96 @@
+"""GPU parity of stages 1-2 (histogram/proportions, median centroids, cdist) against the oracle.
+Everything goes through the C ABI (pilot_b200.ops).  Bit-exact for integer work and proportions."""
+import numpy as np
+import pandas as pd
+import pytest
+import scipy.spatial.distance as ssd
+import torch
+
+from oracle import pilot_oracle as po
+from pilot_b200 import ops, synth, tl
+
+pytestmark = pytest.mark.gpu
+
+
+def dev(x):
+    return torch.from_numpy(np.ascontiguousarray(x)).cuda()
+
+
+@pytest.mark.parametrize("n,K,S", [(0, 3, 2), (1, 1, 1), (3, 2, 2), (1001, 7, 5), (200_003, 10, 20),
+                                   (300_000, 64, 2000), (50_000, 200, 300)])
+def test_hist_counts_and_first_index(n, K, S):
+    rng = np.random.default_rng(n + K)
+    ct = rng.integers(0, K, size=n).astype(np.int32)
+    sm = rng.integers(0, S, size=n).astype(np.int32)
+    if n > 10:  # leave some codes unused
+        ct[ct == K - 1] = 0
+    counts, fct, fsm = ops.hist(dev(ct), dev(sm), K, S)
+    want = np.bincount(sm.astype(np.int64) * K + ct, minlength=S * K).reshape(S, K)
+    assert np.array_equal(counts.cpu().numpy(), want)
+    wf = np.full(K, n, dtype=np.int64)
+    np.minimum.at(wf, ct, np.arange(n))
+    ws = np.full(S, n, dtype=np.int64)
+    np.minimum.at(ws, sm, np.arange(n))
+    assert np.array_equal(fct.cpu().numpy(), wf)
+    assert np.array_equal(fsm.cpu().numpy(), ws)
+
+
+@pytest.mark.parametrize("labels", ["str", "categorical", "int"])
+@pytest.mark.parametrize("regulizer,normalization", [(0.2, True), (1.3, True), (0.2, False)])
+def test_cluster_representations_bit_exact(labels, regulizer, normalization):
+    X, obs = synth.make_cells(60_000, 4, 13, 37, 17, labels=labels)
+    annot = obs.rename(columns={"cell_types": "cell_type"})
+    got = tl.Cluster_Representations(annot, regulizer=regulizer, normalization=normalization)
+    want = po.cluster_representations(annot, regulizer=regulizer, normalization=normalization)
+    assert list(got.keys()) == list(want.keys())
+    for k in want:
+        assert got[k].dtype == np.float64
+        assert np.array_equal(got[k], want[k]), k
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+@pytest.mark.parametrize("n,K,D", [(1, 1, 1), (2, 1, 3), (7, 2, 5), (5000, 6, 9), (120_001, 10, 30)])
+def test_centroid_median_bit_exact(dtype, n, K, D):
+    rng = np.random.default_rng(n * 7 + D)
+    X = rng.normal(size=(n, D)).astype(dtype)
+    if n >= 5000:
+        X[rng.integers(0, n, 200), rng.integers(0, D, 200)] = np.nan      # NaNs are skipped
+        X[: n // 3, 0] = np.round(X[: n // 3, 0], 1)                      # heavy duplicates
+        X[:, 1] = np.abs(X[:, 1]) * (rng.random(n) < 0.5)                 # zero inflated
+    code = rng.integers(0, K, size=n).astype(np.int32)
+    code[:K] = np.arange(K)  # every type present
+    cent, cent64 = ops.centroid_median(dev(X), dev(code), K)
+    want = np.stack([np.nanmedian(X[code == k], axis=0) for k in range(K)])
+    assert cent.cpu().numpy().dtype == dtype
+    np.testing.assert_array_equal(cent.cpu().numpy(), want.astype(dtype))
+    np.testing.assert_array_equal(cent64.cpu().numpy(), want.astype(np.float64))
+
+
+@pytest.mark.parametrize("metric", ["cosine", "euclidean", "sqeuclidean", "cityblock", "chebyshev", "correlation"])
+def test_cdist_matches_scipy(metric):
+    rng = np.random.default_rng(4)
+    C = rng.normal(size=(37, 50))
+    cost, cost_norm, cmax = ops.cdist(dev(C), metric)
+    want = ssd.squareform(ssd.pdist(C, metric))
+    np.testing.assert_allclose(cost.cpu().numpy(), want, rtol=1e-12, atol=1e-14)
+    got = cost.cpu().numpy()
+    assert np.array_equal(cost_norm.cpu().numpy(), got / got.max())
+    assert cmax.item() == got.max()
+    assert np.array_equal(got, got.T) and (np.diag(got) == 0).all()
+
+
+def test_cdist_unknown_metric_raises():
+    with pytest.raises(ValueError):
+        ops.cdist(dev(np.zeros((3, 3))), "jaccard")
+
+
+@pytest.mark.parametrize("labels", ["str", "categorical"])
+def test_cost_matrix_matches_oracle(labels):
+    X, obs = synth.make_cells(80_000, 20, 9, 12, 5, labels=labels)
+    annot = obs.rename(columns={"cell_types": "cell_type"})
+    data = pd.DataFrame(X)
+    dis, cost = tl.cost_matrix(annot, data, metric="cosine")
+    wdis, wcost = po.cost_matrix(annot, data, metric="cosine")
+    np.testing.assert_allclose(dis, wdis, rtol=1e-12, atol=1e-15)
+    pd.testing.assert_index_equal(cost.index, wcost.index)
+    assert list(cost.columns) == list(wcost.columns)

@@ -1,0 +1,83 @@
+"""Host-side glue of pilot_b200.tl (no GPU needed): factorisation helpers and the pandas
+containers of the adata.uns contract."""
+import numpy as np
+import pandas as pd
+import pytest
+
+from oracle import pilot_oracle as po
+from pilot_b200 import synth, tl
+
+
+def first_appearance_perm(codes, n_codes):
+    first = np.full(n_codes, len(codes), dtype=np.int64)
+    np.minimum.at(first, codes, np.arange(len(codes)))
+    p = np.argsort(first, kind="stable")
+    return p[first[p] < len(codes)].astype(np.int32)
+
+
+@pytest.mark.parametrize("labels", ["str", "categorical", "int"])
+def test_unique_in_order_equals_pandas_unique(labels):
+    X, obs = synth.make_cells(5000, 3, 9, 14, 3, labels=labels)
+    if labels == "categorical":
+        obs["cell_types"] = obs["cell_types"].cat.add_categories(["never_seen"])
+    for name in ("cell_types", "sampleID"):
+        col = obs[name]
+        codes, lab = tl._raw_codes(col)
+        assert codes.dtype == np.int32 and codes.min() >= 0
+        perm = first_appearance_perm(codes, len(lab))
+        mine = tl._unique_in_order(col, lab, perm)
+        ref = col.unique()
+        assert type(mine) is type(ref)
+        assert list(mine) == list(ref)
+        f1 = pd.DataFrame(np.zeros((len(perm), len(perm))))
+        f1.columns = mine
+        f2 = pd.DataFrame(np.zeros((len(perm), len(perm))))
+        f2.columns = ref
+        pd.testing.assert_index_equal(f1.columns, f2.columns)
+
+
+def test_missing_labels_rejected():
+    with pytest.raises(ValueError):
+        tl._raw_codes(pd.Series(["a", None, "b"], name="cell_type"))
+
+
+def test_frames_match_reference_assembly():
+    P, M = synth.make_pairs(5, 4, seed=1)
+    ids = [f"p{i}" for i in range(5)]
+    EMD = np.arange(25, dtype=float).reshape(5, 5)
+    mine = tl._emd_frame(EMD, ids)
+    ref = pd.DataFrame.from_dict(EMD).T
+    ref.columns = ids
+    ref["sampleID"] = ids
+    ref = ref.set_index("sampleID")
+    pd.testing.assert_frame_equal(mine, ref)
+    cells = np.array(["a", "b", "c", "d"], dtype=object)
+    c1 = tl._cost_frame(M, cells)
+    assert c1.index.name == "cell_types" and list(c1.columns) == list(cells)
+    np.testing.assert_array_equal(c1.to_numpy(), M)
+
+
+def test_return_real_labels_matches_oracle():
+    X, obs = synth.make_cells(3000, 3, 4, 11, 8)
+    annot = obs.rename(columns={"cell_types": "cell_type"})
+    assert tl.return_real_labels(annot) == po.return_real_labels(annot)
+
+
+def test_emd_mass_check_like_pot():
+    P = np.array([[0.5, 0.5], [0.6, 0.4 + 1e-5]])
+    with pytest.raises(AssertionError):
+        tl._check_emd_inputs(P, np.zeros((2, 2)))
+    tl._check_emd_inputs(np.array([[0.5, 0.5], [0.25, 0.75]]), np.zeros((2, 2)))
+
+
+def test_extract_mirrors_reference_columns(tmp_path):
+    adata = synth.make_adata("c1", scale=0.001)
+    data, annot = tl.extract_data_anno_scRNA_from_h5ad(adata, emb_matrix="X_PCA", clusters_col="cell_types",
+                                                       sample_col="sampleID", status="status")
+    assert list(annot.columns) == ["cell_type", "sampleID", "status"]
+    assert list(data.columns)[:2] == ["PCA_1", "PCA_2"] and data.shape[1] == 30
+    assert tl.path_to_results == "Results_PILOT/plots"
+    import os
+    assert os.path.isdir("Results_PILOT/plots")
+    with pytest.raises(KeyError):
+        tl.extract_data_anno_scRNA_from_h5ad(adata, emb_matrix="missing")
