@@ -27,19 +27,19 @@ __global__ void __launch_bounds__(256) fma_peak_kernel(T *out, T seed)
 
 __global__ void __launch_bounds__(256) dmma_peak_kernel(double *out, double seed)
 {
-    double c0[4] = {0, 0, 0, 0}, c1[4] = {0, 0, 0, 0};  // two independent 8x8 accumulators x 2
-    double a = seed + threadIdx.x, b = seed * 0.5 + threadIdx.x;
+    double c[PEAK_ILP][2];
+#pragma unroll
+    for (int i = 0; i < PEAK_ILP; ++i) { c[i][0] = 0.0; c[i][1] = 0.0; }
+    const double a = seed + threadIdx.x * 1e-3, b = seed * 0.5 + threadIdx.x * 1e-3;
     for (int it = 0; it < PEAK_ITERS; ++it) {
-        asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
-                     : "+d"(c0[0]), "+d"(c0[1]) : "d"(a), "d"(b));
-        asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
-                     : "+d"(c0[2]), "+d"(c0[3]) : "d"(a), "d"(b));
-        asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
-                     : "+d"(c1[0]), "+d"(c1[1]) : "d"(a), "d"(b));
-        asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
-                     : "+d"(c1[2]), "+d"(c1[3]) : "d"(a), "d"(b));
+#pragma unroll
+        for (int i = 0; i < PEAK_ILP; ++i)
+            asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                         : "+d"(c[i][0]), "+d"(c[i][1]) : "d"(a), "d"(b));
     }
-    double s = c0[0] + c0[1] + c0[2] + c0[3] + c1[0] + c1[1] + c1[2] + c1[3];
+    double s = 0.0;
+#pragma unroll
+    for (int i = 0; i < PEAK_ILP; ++i) s += c[i][0] + c[i][1];
     if (s == 12345.678) out[0] = s;
 }
 
@@ -68,7 +68,7 @@ extern "C" int pilot_pipe_peak(int kind, double *h_tflops, void *stream)
         PILOT_CUDA(cudaEventElapsedTime(&ms, e0, e1));
         double flops;
         if (kind <= 1) flops = 2.0 * PEAK_ITERS * PEAK_ILP * (double)ctas * th;
-        else flops = 2.0 * 8 * 8 * 4 * 4.0 * PEAK_ITERS * (double)ctas * (th / 32);
+        else flops = 2.0 * 8 * 8 * 4 * (double)PEAK_ILP * PEAK_ITERS * (double)ctas * (th / 32);
         const double tf = flops / (ms * 1e-3) / 1e12;
         if (rep > 0 && tf > best) best = tf;
     }

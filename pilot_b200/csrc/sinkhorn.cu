@@ -54,12 +54,17 @@ extern "C" int pilot_sinkhorn_pairs(const double *props, int S, int K, const dou
     ws.setup = (double *)(p + 256);
     ws.scratch = (double *)(p + 256 + skb_setup_bytes(KP));
     ws.redo = (long long *)(p + 256 + skb_setup_bytes(KP) + skb_scratch_bytes(KP, sm_count()));
-    // persistent grid: one CTA per SM, fewer when there is less than one slot-load of work
-    const int slots_per_cta = 8 * (32 / (KP / 8)) * 4;
-    long long ctas = (pm.n_local + slots_per_cta - 1) / slots_per_cta;
+    // persistent grid: one CTA per SM; with little work, spread it over all SMs by capping the
+    // number of live slots per lane group (latency, not throughput, is what matters then)
+    const long long groups = (long long)sm_count() * (skb_slots_per_cta() / 4);
+    int slot_cap = (int)((pm.n_local + groups - 1) / groups);
+    if (slot_cap > 4) slot_cap = 4;
+    if (slot_cap < 1) slot_cap = 1;
+    const long long per_cta = (long long)(skb_slots_per_cta() / 4) * slot_cap;
+    long long ctas = (pm.n_local + per_cta - 1) / per_cta;
     if (ctas > sm_count()) ctas = sm_count();
-    rc = skb_launch(props, K, cost, prm, pm, ws.setup, ws.scratch, (int)ctas, out, iters, absorptions, status,
-                    ws.counter_fast, ws.redo, ws.n_redo, st);
+    rc = skb_launch(props, K, cost, prm, pm, ws.setup, ws.scratch, (int)ctas, slot_cap, out, iters, absorptions,
+                    status, ws.counter_fast, ws.redo, ws.n_redo, st);
     if (rc) return rc;
     // problems the scaled form could not represent (normally none): reference-form kernel
     return sinkhorn_ref_launch(props, K, cost, prm, pm, ws.redo, ws.n_redo, SK_REDO_CAP, out, iters, absorptions,

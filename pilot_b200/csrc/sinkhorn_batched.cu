@@ -13,26 +13,26 @@
 // result is sum_ij M_ij K0_ij ut_i vt_j.  Rounding differs from the reference form at the
 // 1e-16 level with identical iteration/absorption schedules.
 //
-// Mapping.  The two matvecs for many problems are K0^T [ut_1 .. ut_P] and K0 [vt_1 .. vt_P]:
-// register-tiled FP64 GEMMs.  A group of NTJ = KP/8 adjacent lanes owns 4 problem "slots";
-// each lane accumulates an 8 (rows) x 4 (slots) tile, A-fragments (K0 rows) and B-fragments
-// (slot vectors) come from shared memory as 128-bit loads: 6 LDS.128 per 32 DFMA.  All
-// traffic for one slot stays inside its warp, so warps are independent persistent workers
-// (no CTA barrier in the loop); a finished slot is refilled at once from a global counter.
-// Problems the scaled form cannot represent (NaN, |log ut| near the FP64 range) are queued
+// Mapping.  The two matvecs of 8 problems ("slots") at a time are the dense FP64 GEMMs
+// K0^T [ut_1 .. ut_8] and K0 [vt_1 .. vt_8]; each warp runs them on the FP64 tensor path
+// (mma.sync m8n8k4, DMMA): KP/8 accumulator tiles per warp, A fragments from the shared
+// K0 / K0^T (XOR-swizzled: 2 wavefronts per fragment load, the minimum for 256 B), B fragments
+// from the warp's private 8-column U / V panel (64-byte rows: conflict free as they are).  In
+// the C-fragment layout lane (g = lane/4, t = lane%4) owns rows {8m+g} of the adjacent slots
+// {2t, 2t+1}, so the element-wise update (one 128-bit store per row), the max/err reductions
+// (3 xor-shuffles over the 8 lanes sharing t) and all per-slot state stay inside the warp: the
+// 16 warps of a CTA are independent persistent workers, no CTA barrier in the loop, a finished
+// slot is refilled at once from a global counter.  DMMA has the same peak as DFMA on B200
+// (measured 37 TFLOP/s both) but needs 1/8 of the issue slots; with 4 warps per scheduler the
+// epilogue (FP64 pipe, LSU) of three warps overlaps the DMMA stream of the fourth.
+// Problems the scaled form cannot represent (NaN/Inf, |log ut| near the FP64 range) are queued
 // for the reference-form kernel (sinkhorn_ref.cu).
 #include "sinkhorn.cuh"
 
 namespace pilot {
 
-constexpr int SKB_WARPS = 8;
-
-template <int KP> struct SkbCfg {
-    static constexpr int NTJ = KP / 8;    // lanes per slot group
-    static constexpr int GPW = 32 / NTJ;  // groups per warp
-    static constexpr int SPW = GPW * 4;   // slots per warp
-    static constexpr int PS = SPW;        // row stride (doubles) of the per-warp U / V panels
-};
+constexpr int SKB_WARPS = 16;
+constexpr int SKB_SPW = 8;  // slots (problems in flight) per warp = panel columns
 
 // K0, K0^T, M o K0 (all KP x KP, zero padded) and c0 = K0^T (1/K) into the workspace
 __global__ void skb_setup_kernel(const double *__restrict__ M, int K, int KP, double reg,
@@ -62,134 +62,162 @@ __global__ void skb_setup_kernel(const double *__restrict__ M, int K, int KP, do
         }
 }
 
-template <int KP>
+__device__ __forceinline__ void dmma884(double &c0, double &c1, double a, double b)
+{
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                 : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+}
+
+// branch-free x / y for finite positive y: 20-bit seed, two Newton steps, one residual correction
+__device__ __forceinline__ double fast_div(double x, double y)
+{
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(y));
+    double e = fma(-y, r, 1.0);
+    r = fma(r, e, r);
+    e = fma(-y, r, 1.0);
+    r = fma(r, e, r);
+    const double q = x * r;
+    return fma(fma(-y, q, x), r, q);
+}
+
+// swizzled panel / matrix addressing: column ^ 8 on odd rows
+__device__ __forceinline__ int swz(int row, int col) { return col ^ ((row & 1) << 3); }
+
+template <int KP, bool FULL>
 __global__ void __launch_bounds__(SKB_WARPS * 32, 1)
-sinkhorn_batched_kernel(const double *__restrict__ props, int K, SkParams prm, PairMap pm,
+sinkhorn_batched_kernel(const double *__restrict__ props, int K, SkParams prm, PairMap pm, int slot_cap,
                         const double *__restrict__ gK0, const double *__restrict__ gK0T,
                         const double *__restrict__ gMK, const double *__restrict__ gc0,
-                        double *__restrict__ scratch,  // [gridDim * WARPS * SPW][2][KP] rea / reb
+                        double *__restrict__ scratch,  // [gridDim * WARPS * 8][2][KP] rea / reb
                         double *__restrict__ out, int *__restrict__ iters_out, int *__restrict__ abs_out,
                         int *__restrict__ status_out, unsigned long long *__restrict__ counter,
                         long long *__restrict__ redo_list, unsigned long long *__restrict__ n_redo)
 {
-    using C = SkbCfg<KP>;
-    constexpr int NTJ = C::NTJ, SPW = C::SPW, PS = C::PS;
+    constexpr int MT = KP / 8;   // accumulator row tiles
+    constexpr int KS = KP / 4;   // k-steps of 4
+    constexpr int PS = SKB_SPW;  // panel row stride (doubles): 64-byte rows, conflict-free as they are
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    double *sK0 = reinterpret_cast<double *>(smem_raw);
-    double *sK0T = sK0 + KP * KP;
+    double *sK0 = reinterpret_cast<double *>(smem_raw);  // [i][swz(i, j)]
+    double *sK0T = sK0 + KP * KP;                        // [j][swz(j, i)]
     double *sc0 = sK0T + KP * KP;
     double *sUV = sc0 + KP;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    double *U = sUV + (size_t)warp * 2 * KP * PS;  // U[k][PS], then V[k][PS]
+    double *U = sUV + (size_t)warp * 2 * KP * PS;  // U[row][slot], then V
     double *V = U + KP * PS;
-    for (int e = threadIdx.x; e < KP * KP; e += blockDim.x) { sK0[e] = gK0[e]; sK0T[e] = gK0T[e]; }
+    for (int e = threadIdx.x; e < KP * KP; e += blockDim.x) {
+        const int r = e / KP, c = e - r * KP;
+        sK0[r * KP + swz(r, c)] = gK0[e];
+        sK0T[r * KP + swz(r, c)] = gK0T[e];
+    }
     for (int e = threadIdx.x; e < KP; e += blockDim.x) sc0[e] = gc0[e];
     __syncthreads();
 
-    const int tj = lane % NTJ, grp = lane / NTJ;
-    const unsigned gmask = (NTJ == 32 ? 0xffffffffu : ((1u << NTJ) - 1u)) << (grp * NTJ);
-    const int col0 = grp * 4;  // first slot column of this group inside the warp panel
-    double *wscr = scratch + ((size_t)(blockIdx.x * SKB_WARPS + warp) * SPW) * 2 * KP;
-    // rows owned by this lane: j(q,h) = 2*NTJ*q + 2*tj + h
-    int rowj[8];
-#pragma unroll
-    for (int q = 0; q < 4; ++q) { rowj[2 * q] = 2 * NTJ * q + 2 * tj; rowj[2 * q + 1] = rowj[2 * q] + 1; }
+    // C-fragment ownership: lane (g, t) holds rows {8m + g} of the slots {2t, 2t + 1}
+    const int g = lane >> 2, t = lane & 3;
+    const unsigned gmask = 0x11111111u << t;  // the 8 lanes that share my 2 slots
+    const int tsw = (t & 1) << 3;             // K0 fragment rows 4*ks + t have the parity of t
+    double *wscr = scratch + ((size_t)(blockIdx.x * SKB_WARPS + warp) * SKB_SPW) * 2 * KP;
+    double *rea0 = wscr + (size_t)(2 * t) * 2 * KP;  // slot 2t: rea, then reb; slot 2t+1 follows
     const double invK = 1.0 / K;
+    double *Uc = U + g * PS + 2 * t;  // my first element of U; rows advance by 8 * PS
+    double *Vc = V + g * PS + 2 * t;
 
-    // per-slot state, replicated in the NTJ lanes of the group
-    long long sl[4];
-    int s_i[4], s_j[4], s_ii[4], s_abs[4];
-    bool s_act[4], s_hasabs[4], s_pend[4], s_force[4], s_fresh[4], s_bad[4];
+    // per-slot state (h = 0, 1), replicated in the 8 lanes of the group
+    long long sl[2];
+    const double *pa[2], *pb[2];
+    int s_ii[2], s_abs[2];
+    bool s_act[2], s_hasabs[2], s_pend[2], s_force[2], s_fresh[2], s_bad[2];
+
+#define ROW_OK(r) (FULL || (r) < K)
+#define SKB_ASSIGN(h, w)                                                                    \
+    do {                                                                                    \
+        sl[h] = (long long)(w);                                                             \
+        s_act[h] = (w) != ~0ULL && (long long)(w) < pm.n_local;                             \
+        int si_ = 0, sj_ = 0;                                                               \
+        if (s_act[h]) global_to_ij(pm, local_to_global(pm, sl[h]), si_, sj_);               \
+        pa[h] = props + (long long)si_ * K + g;                                             \
+        pb[h] = props + (long long)sj_ * K + g;                                             \
+        s_ii[h] = 0; s_abs[h] = 0; s_hasabs[h] = false; s_pend[h] = false; s_force[h] = false; \
+        s_fresh[h] = true; s_bad[h] = false;                                                \
+        _Pragma("unroll") for (int m = 0; m < MT; ++m) {                                    \
+            const double v0 = (s_act[h] && ROW_OK(8 * m + g)) ? invK : 0.0;                 \
+            Uc[8 * m * PS + h] = v0;                                                        \
+            Vc[8 * m * PS + h] = v0;                                                        \
+        }                                                                                   \
+    } while (0)
 
     // initial fill
 #pragma unroll
-    for (int c = 0; c < 4; ++c) {
-        unsigned long long w = 0;
-        if (tj == 0) w = atomicAdd(counter, 1ULL);
-        w = __shfl_sync(gmask, w, grp * NTJ);
-        sl[c] = (long long)w; s_i[c] = 0; s_j[c] = 0;
-        s_act[c] = (long long)w < pm.n_local;
-        if (s_act[c]) global_to_ij(pm, local_to_global(pm, sl[c]), s_i[c], s_j[c]);
-        s_ii[c] = 0; s_abs[c] = 0; s_hasabs[c] = false; s_pend[c] = false; s_force[c] = false;
-        s_fresh[c] = true; s_bad[c] = false;
-#pragma unroll
-        for (int r = 0; r < 8; ++r) {
-            U[rowj[r] * PS + col0 + c] = (s_act[c] && rowj[r] < K) ? invK : 0.0;
-            V[rowj[r] * PS + col0 + c] = (s_act[c] && rowj[r] < K) ? invK : 0.0;
-        }
+    for (int h = 0; h < 2; ++h) {
+        unsigned long long w = ~0ULL;
+        if (g == 0 && h < slot_cap) w = atomicAdd(counter, 1ULL);
+        w = __shfl_sync(gmask, w, t);
+        SKB_ASSIGN(h, w);
     }
     __syncwarp();
 
     for (;;) {
-        bool any_act = false;
-#pragma unroll
-        for (int c = 0; c < 4; ++c) any_act |= s_act[c];
-        if (!__any_sync(0xffffffffu, any_act)) break;
+        if (!__any_sync(0xffffffffu, s_act[0] || s_act[1])) break;
 
-        double acc[8][4];
+        double acc[MT][2];
+        double num[MT][2];
         // ======================= phase A: T = K0^T Ut =======================
 #pragma unroll
-        for (int r = 0; r < 8; ++r)
+        for (int m = 0; m < MT; ++m) { acc[m][0] = 0.0; acc[m][1] = 0.0; }
+#pragma unroll 2
+        for (int ks = 0; ks < KS; ++ks) {
+            const int kr = 4 * ks + t;
+            const double b0 = U[kr * PS + g];
+            const double *arow = sK0 + kr * KP + g;
 #pragma unroll
-            for (int c = 0; c < 4; ++c) acc[r][c] = 0.0;
-#pragma unroll 4
-        for (int k = 0; k < KP; ++k) {
-            double a[8], b[4];
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                const double2 t2 = *reinterpret_cast<const double2 *>(sK0 + k * KP + 2 * NTJ * q + 2 * tj);
-                a[2 * q] = t2.x; a[2 * q + 1] = t2.y;
-            }
-            {
-                const double2 b0 = *reinterpret_cast<const double2 *>(U + k * PS + col0);
-                const double2 b1 = *reinterpret_cast<const double2 *>(U + k * PS + col0 + 2);
-                b[0] = b0.x; b[1] = b0.y; b[2] = b1.x; b[3] = b1.y;
-            }
-#pragma unroll
-            for (int r = 0; r < 8; ++r)
-#pragma unroll
-                for (int c = 0; c < 4; ++c) acc[r][c] = fma(a[r], b[c], acc[r][c]);
+            for (int m = 0; m < MT; ++m) dmma884(acc[m][0], acc[m][1], arow[(8 * m) ^ tsw], b0);
         }
+        // numerators of the v-update: b of my two slots
+#pragma unroll
+        for (int h = 0; h < 2; ++h)
+#pragma unroll
+            for (int m = 0; m < MT; ++m)
+                num[m][h] = (s_act[h] && ROW_OK(8 * m + g)) ? __ldg(pb[h] + 8 * m) : 0.0;
 
         // ---- resolve the pending convergence check / iteration cap of the previous iteration ----
-        bool stop[4];
-        int stop_status[4];
+        bool stop[2];
+        int stop_status[2];
 #pragma unroll
-        for (int c = 0; c < 4; ++c) {
-            stop[c] = false; stop_status[c] = PILOT_ST_MAXITER;
-            if (s_act[c] && !s_fresh[c]) {
-                if (s_bad[c]) {
-                    stop[c] = true; stop_status[c] = -1;  // handed to the reference-form kernel
+        for (int h = 0; h < 2; ++h) {
+            stop[h] = false; stop_status[h] = PILOT_ST_MAXITER;
+            if (s_act[h] && !s_fresh[h]) {
+                if (s_bad[h]) {
+                    stop[h] = true; stop_status[h] = -1;  // handed to the reference-form kernel
                 } else {
                     bool conv = false;
-                    if (s_pend[c]) {
+                    if (s_pend[h]) {
                         double e2 = 0.0;
 #pragma unroll
-                        for (int r = 0; r < 8; ++r)
-                            if (rowj[r] < K) {
-                                const double bj = __ldg(props + (long long)s_j[c] * K + rowj[r]);
-                                const double d = fma(V[rowj[r] * PS + col0 + c], acc[r][c], -bj);
+                        for (int m = 0; m < MT; ++m)
+                            if (ROW_OK(8 * m + g)) {
+                                const double d = fma(Vc[8 * m * PS + h], acc[m][h], -num[m][h]);
                                 e2 = fma(d, d, e2);
                             }
-#pragma unroll
-                        for (int o = 1; o < NTJ; o <<= 1) e2 += __shfl_xor_sync(gmask, e2, o);
+                        e2 += __shfl_xor_sync(gmask, e2, 4);
+                        e2 += __shfl_xor_sync(gmask, e2, 8);
+                        e2 += __shfl_xor_sync(gmask, e2, 16);
                         conv = sqrt(e2) <= prm.stop_thr;
                     }
-                    if (conv) { stop[c] = true; stop_status[c] = PILOT_ST_CONVERGED; }
-                    else if (s_force[c]) { stop[c] = true; stop_status[c] = PILOT_ST_MAXITER; }
+                    if (conv) { stop[h] = true; stop_status[h] = PILOT_ST_CONVERGED; }
+                    else if (s_force[h]) { stop[h] = true; stop_status[h] = PILOT_ST_MAXITER; }
                 }
             }
         }
         // ---- warp-cooperative finalisation + refill of the stopped slots ----
 #pragma unroll
-        for (int c = 0; c < 4; ++c) {
-            unsigned m = __ballot_sync(0xffffffffu, stop[c]);
-            while (m) {
-                const int src = __ffs(m) - 1;              // first lane of a stopping group
-                const int g = src / NTJ;
-                m &= ~(((NTJ == 32) ? 0xffffffffu : ((1u << NTJ) - 1u)) << (g * NTJ));
-                const int col = g * 4 + c;
-                const int stt = __shfl_sync(0xffffffffu, stop_status[c], src);
+        for (int h = 0; h < 2; ++h) {
+            unsigned mball = __ballot_sync(0xffffffffu, stop[h]) & 0xfu;  // one bit per group (lanes 0..3)
+            while (mball) {
+                const int tt = __ffs(mball) - 1;  // group id == its t
+                mball &= mball - 1;
+                const int col = 2 * tt + h;
+                const int stt = __shfl_sync(0xffffffffu, stop_status[h], tt);
                 double cost = 0.0;
                 if (stt >= 0) {
                     // cost = sum_j Vt_j * sum_i (M o K0)_ij Ut_i ; lane = column j
@@ -203,184 +231,195 @@ sinkhorn_batched_kernel(const double *__restrict__ props, int K, SkParams prm, P
                 unsigned long long w = 0;
                 if (lane == 0) w = atomicAdd(counter, 1ULL);
                 w = __shfl_sync(0xffffffffu, w, 0);
-                const bool mine = grp == g;
-                if (mine && tj == 0) {
+                const bool mine = t == tt;
+                if (mine && g == 0) {
                     if (stt >= 0) {
-                        out[sl[c]] = cost;
-                        if (iters_out) iters_out[sl[c]] = s_ii[c];
-                        if (abs_out) abs_out[sl[c]] = s_abs[c];
-                        if (status_out) status_out[sl[c]] = stt;
+                        out[sl[h]] = cost;
+                        if (iters_out) iters_out[sl[h]] = s_ii[h];
+                        if (abs_out) abs_out[sl[h]] = s_abs[h];
+                        if (status_out) status_out[sl[h]] = stt;
                     } else {
                         const unsigned long long slot = atomicAdd(n_redo, 1ULL);
-                        if ((long long)slot < SK_REDO_CAP) redo_list[slot] = sl[c];
-                        out[sl[c]] = __longlong_as_double(0x7ff8000000000000LL);
-                        if (status_out) status_out[sl[c]] = -1;
+                        if ((long long)slot < SK_REDO_CAP) redo_list[slot] = sl[h];
+                        out[sl[h]] = __longlong_as_double(0x7ff8000000000000LL);
+                        if (status_out) status_out[sl[h]] = -1;
                     }
                 }
                 if (mine) {
-                    sl[c] = (long long)w;
-                    s_act[c] = (long long)w < pm.n_local;
-                    if (s_act[c]) global_to_ij(pm, local_to_global(pm, sl[c]), s_i[c], s_j[c]);
-                    s_ii[c] = 0; s_abs[c] = 0; s_hasabs[c] = false; s_pend[c] = false; s_force[c] = false;
-                    s_fresh[c] = true; s_bad[c] = false;
+                    SKB_ASSIGN(h, w);
 #pragma unroll
-                    for (int r = 0; r < 8; ++r) {
-                        U[rowj[r] * PS + col0 + c] = (s_act[c] && rowj[r] < K) ? invK : 0.0;
-                        V[rowj[r] * PS + col0 + c] = (s_act[c] && rowj[r] < K) ? invK : 0.0;
-                    }
+                    for (int m = 0; m < MT; ++m)
+                        num[m][h] = (s_act[h] && ROW_OK(8 * m + g)) ? __ldg(pb[h] + 8 * m) : 0.0;
                 }
             }
         }
         __syncwarp();
 
-        // ---- v-update: Vt = b / T ----
-        double mxv[4];
-        bool badv[4];
+        // ---- v-update: Vt = b / T (my two slots are adjacent: one 128-bit store per row) ----
+        double mxv[2] = {0.0, 0.0}, smv[2] = {0.0, 0.0};
+        if (s_act[0] || s_act[1]) {
 #pragma unroll
-        for (int c = 0; c < 4; ++c) {
-            mxv[c] = 0.0; badv[c] = false;
-            if (s_act[c]) {
-                const double *reb = wscr + ((size_t)(col0 + c) * 2 + 1) * KP;
+            for (int m = 0; m < MT; ++m) {
+                const int row = 8 * m + g;
+                double vv[2] = {0.0, 0.0};
+                if (ROW_OK(row)) {
 #pragma unroll
-                for (int r = 0; r < 8; ++r) {
-                    const int j = rowj[r];
-                    if (j < K) {
-                        const double t = s_fresh[c] ? sc0[j] : acc[r][c];
-                        const double bj = __ldg(props + (long long)s_j[c] * K + j);
-                        const double vn = bj / t;
-                        V[j * PS + col0 + c] = vn;
-                        const double uu = s_hasabs[c] ? vn * reb[j] : vn;
-                        badv[c] |= (vn != vn) || (uu != uu);
-                        mxv[c] = fmax(mxv[c], fabs(uu));
-                    }
+                    for (int h = 0; h < 2; ++h)
+                        if (s_act[h]) {
+                            const double tv = s_fresh[h] ? sc0[row] : acc[m][h];
+                            vv[h] = fast_div(num[m][h], tv);
+                            const double uu = s_hasabs[h] ? vv[h] * rea0[(2 * h + 1) * KP + row] : vv[h];
+                            mxv[h] = fmax(mxv[h], fabs(uu));
+                            smv[h] += uu;
+                        }
                 }
+                *reinterpret_cast<double2 *>(Vc + 8 * m * PS) = make_double2(vv[0], vv[1]);
             }
         }
         __syncwarp();
 
         // ======================= phase B: S = K0 Vt =======================
 #pragma unroll
-        for (int r = 0; r < 8; ++r)
+        for (int m = 0; m < MT; ++m) { acc[m][0] = 0.0; acc[m][1] = 0.0; }
+#pragma unroll 2
+        for (int ks = 0; ks < KS; ++ks) {
+            const int kr = 4 * ks + t;
+            const double b0 = V[kr * PS + g];
+            const double *arow = sK0T + kr * KP + g;
 #pragma unroll
-            for (int c = 0; c < 4; ++c) acc[r][c] = 0.0;
-#pragma unroll 4
-        for (int k = 0; k < KP; ++k) {
-            double a[8], b[4];
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                const double2 t2 = *reinterpret_cast<const double2 *>(sK0T + k * KP + 2 * NTJ * q + 2 * tj);
-                a[2 * q] = t2.x; a[2 * q + 1] = t2.y;
-            }
-            {
-                const double2 b0 = *reinterpret_cast<const double2 *>(V + k * PS + col0);
-                const double2 b1 = *reinterpret_cast<const double2 *>(V + k * PS + col0 + 2);
-                b[0] = b0.x; b[1] = b0.y; b[2] = b1.x; b[3] = b1.y;
-            }
-#pragma unroll
-            for (int r = 0; r < 8; ++r)
-#pragma unroll
-                for (int c = 0; c < 4; ++c) acc[r][c] = fma(a[r], b[c], acc[r][c]);
+            for (int m = 0; m < MT; ++m) dmma884(acc[m][0], acc[m][1], arow[(8 * m) ^ tsw], b0);
         }
         // ---- u-update: Ut = a / S, then the per-slot service (absorption, counters) ----
+        if (s_act[0] || s_act[1]) {
 #pragma unroll
-        for (int c = 0; c < 4; ++c) {
-            if (s_act[c]) {
-                double *rea = wscr + ((size_t)(col0 + c) * 2) * KP;
-                double *reb = rea + KP;
-                double mxu = 0.0;
-                bool bad = badv[c];
-                double un[8];
+            for (int h = 0; h < 2; ++h)
 #pragma unroll
-                for (int r = 0; r < 8; ++r) {
-                    const int i = rowj[r];
-                    un[r] = 0.0;
-                    if (i < K) {
-                        const double ai = __ldg(props + (long long)s_i[c] * K + i);
-                        un[r] = ai / acc[r][c];
-                        const double uu = s_hasabs[c] ? un[r] * rea[i] : un[r];
-                        bad |= (un[r] != un[r]) || (uu != uu);
-                        mxu = fmax(mxu, fabs(uu));
+                for (int m = 0; m < MT; ++m)
+                    num[m][h] = (s_act[h] && ROW_OK(8 * m + g)) ? __ldg(pa[h] + 8 * m) : 0.0;
+            double un[MT][2];
+            double mxu[2] = {0.0, 0.0}, smu[2] = {0.0, 0.0};
+#pragma unroll
+            for (int h = 0; h < 2; ++h)
+#pragma unroll
+                for (int m = 0; m < MT; ++m) {
+                    const int row = 8 * m + g;
+                    un[m][h] = 0.0;
+                    if (s_act[h] && ROW_OK(row)) {
+                        un[m][h] = fast_div(num[m][h], acc[m][h]);
+                        const double uu = s_hasabs[h] ? un[m][h] * rea0[(2 * h) * KP + row] : un[m][h];
+                        mxu[h] = fmax(mxu[h], fabs(uu));
+                        smu[h] += uu;
                     }
                 }
-                double mxvv = mxv[c];
-                int badi = bad ? 1 : 0;
+            bool absorb[2];
 #pragma unroll
-                for (int o = 1; o < NTJ; o <<= 1) {
-                    mxu = fmax(mxu, __shfl_xor_sync(gmask, mxu, o));
-                    mxvv = fmax(mxvv, __shfl_xor_sync(gmask, mxvv, o));
-                    badi |= __shfl_xor_sync(gmask, badi, o);
+            for (int h = 0; h < 2; ++h) {
+                double mu = mxu[h], mv = mxv[h], sm = smu[h] + smv[h];
+#pragma unroll
+                for (int o = 4; o < 32; o <<= 1) {
+                    mu = fmax(mu, __shfl_xor_sync(gmask, mu, o));
+                    mv = fmax(mv, __shfl_xor_sync(gmask, mv, o));
+                    sm += __shfl_xor_sync(gmask, sm, o);
                 }
-                const bool absorb = !badi && (mxu > prm.tau || mxvv > prm.tau);
-                bool range_bad = false;
-#pragma unroll
-                for (int r = 0; r < 8; ++r) {
-                    const int i = rowj[r];
-                    if (i < K) {
-                        if (absorb) {
-                            const double vo = V[i * PS + col0 + c];
-                            rea[i] = 1.0 / un[r];
-                            reb[i] = 1.0 / vo;
-                            // keep e^{+-alpha/reg} comfortably inside the FP64 range
-                            range_bad |= !(un[r] > 1e-250 && un[r] < 1e250 && vo > 1e-250 && vo < 1e250);
-                            un[r] *= invK;
-                            V[i * PS + col0 + c] = vo * invK;
-                        }
-                        U[i * PS + col0 + c] = un[r];
-                    }
+                const bool bad = !(fabs(sm) < 1.7e308);  // NaN or Inf anywhere in u, v
+                absorb[h] = s_act[h] && !bad && (mu > prm.tau || mv > prm.tau);
+                if (s_act[h]) {
+                    s_bad[h] = bad;
+                    s_pend[h] = (s_ii[h] % prm.check_every) == 0;
+                    ++s_ii[h];
+                    s_force[h] = s_ii[h] >= prm.num_iter_max;
+                    s_fresh[h] = false;
                 }
-                int rb = range_bad ? 1 : 0;
-#pragma unroll
-                for (int o = 1; o < NTJ; o <<= 1) rb |= __shfl_xor_sync(gmask, rb, o);
-                if (absorb) { s_hasabs[c] = true; ++s_abs[c]; }
-                s_bad[c] = badi || rb;
-                s_pend[c] = (s_ii[c] % prm.check_every) == 0;
-                ++s_ii[c];
-                s_force[c] = s_ii[c] >= prm.num_iter_max;
-                s_fresh[c] = false;
             }
+            if (absorb[0] || absorb[1]) {
+                // u = v = 1/K in POT == divide the scaled iterates by K; remember 1/ut, 1/vt
+                int rb[2] = {0, 0};
+#pragma unroll
+                for (int m = 0; m < MT; ++m) {
+                    const int row = 8 * m + g;
+                    double2 vo = *reinterpret_cast<double2 *>(Vc + 8 * m * PS);
+                    if (ROW_OK(row)) {
+#pragma unroll
+                        for (int h = 0; h < 2; ++h)
+                            if (absorb[h]) {
+                                double &vref = h ? vo.y : vo.x;
+                                rea0[(2 * h) * KP + row] = 1.0 / un[m][h];
+                                rea0[(2 * h + 1) * KP + row] = 1.0 / vref;
+                                // keep e^{+-alpha/reg} comfortably inside the FP64 range
+                                rb[h] |= !(un[m][h] > 1e-250 && un[m][h] < 1e250 && vref > 1e-250 && vref < 1e250);
+                                un[m][h] *= invK;
+                                vref *= invK;
+                            }
+                    }
+                    *reinterpret_cast<double2 *>(Vc + 8 * m * PS) = vo;
+                }
+#pragma unroll
+                for (int h = 0; h < 2; ++h)
+                    if (absorb[h]) {
+                        int r = rb[h];
+                        r |= __shfl_xor_sync(gmask, r, 4);
+                        r |= __shfl_xor_sync(gmask, r, 8);
+                        r |= __shfl_xor_sync(gmask, r, 16);
+                        s_hasabs[h] = true;
+                        ++s_abs[h];
+                        s_bad[h] = s_bad[h] || r;
+                    }
+            }
+#pragma unroll
+            for (int m = 0; m < MT; ++m)
+                *reinterpret_cast<double2 *>(Uc + 8 * m * PS) = make_double2(un[m][0], un[m][1]);
         }
         __syncwarp();
     }
+#undef SKB_ASSIGN
+#undef ROW_OK
 }
 
 size_t skb_setup_bytes(int KP) { return sizeof(double) * ((size_t)3 * KP * KP + KP); }
 size_t skb_smem_bytes(int KP)
 {
-    const int SPW = (32 / (KP / 8)) * 4;
-    return sizeof(double) * ((size_t)2 * KP * KP + KP + (size_t)SKB_WARPS * 2 * KP * SPW);
+    return sizeof(double) * ((size_t)2 * KP * KP + KP + (size_t)SKB_WARPS * 2 * KP * SKB_SPW);
 }
 size_t skb_scratch_bytes(int KP, int ctas)
 {
-    const int SPW = (32 / (KP / 8)) * 4;
-    return sizeof(double) * (size_t)ctas * SKB_WARPS * SPW * 2 * KP;
+    return sizeof(double) * (size_t)ctas * SKB_WARPS * SKB_SPW * 2 * KP;
 }
 int skb_pad(int K) { return K <= 16 ? 16 : (K <= 32 ? 32 : 64); }
+int skb_slots_per_cta() { return SKB_WARPS * SKB_SPW; }
 
-template <int KP>
-static int skb_launch_t(const double *props, int K, const SkParams &prm, const PairMap &pm, const double *setup,
-                        double *scratch, int ctas, double *out, int *iters, int *absn, int *status,
-                        unsigned long long *counter, long long *redo, unsigned long long *n_redo, cudaStream_t st)
+template <int KP, bool FULL>
+static int skb_launch_t(const double *props, int K, const SkParams &prm, const PairMap &pm, int slot_cap,
+                        const double *setup, double *scratch, int ctas, double *out, int *iters, int *absn,
+                        int *status, unsigned long long *counter, long long *redo, unsigned long long *n_redo,
+                        cudaStream_t st)
 {
     const size_t smem = skb_smem_bytes(KP);
-    PILOT_CUDA(cudaFuncSetAttribute(sinkhorn_batched_kernel<KP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    PILOT_CUDA(cudaFuncSetAttribute(sinkhorn_batched_kernel<KP, FULL>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    (int)smem));
     const double *K0 = setup, *K0T = K0 + KP * KP, *MK = K0T + KP * KP, *c0 = MK + KP * KP;
-    sinkhorn_batched_kernel<KP><<<ctas, SKB_WARPS * 32, smem, st>>>(props, K, prm, pm, K0, K0T, MK, c0, scratch, out,
-                                                                   iters, absn, status, counter, redo, n_redo);
+    sinkhorn_batched_kernel<KP, FULL><<<ctas, SKB_WARPS * 32, smem, st>>>(
+        props, K, prm, pm, slot_cap, K0, K0T, MK, c0, scratch, out, iters, absn, status, counter, redo, n_redo);
     PILOT_LAUNCH_CHECK();
     return 0;
 }
 
 int skb_launch(const double *props, int K, const double *cost, const SkParams &prm, const PairMap &pm,
-               double *setup, double *scratch, int ctas, double *out, int *iters, int *absn, int *status,
-               unsigned long long *counter, long long *redo, unsigned long long *n_redo, cudaStream_t st)
+               double *setup, double *scratch, int ctas, int slot_cap, double *out, int *iters, int *absn,
+               int *status, unsigned long long *counter, long long *redo, unsigned long long *n_redo,
+               cudaStream_t st)
 {
     const int KP = skb_pad(K);
     skb_setup_kernel<<<8, 256, 0, st>>>(cost, K, KP, prm.reg, setup, setup + KP * KP, setup + 2 * KP * KP,
                                         setup + 3 * KP * KP);
     PILOT_LAUNCH_CHECK();
-    if (KP == 16) return skb_launch_t<16>(props, K, prm, pm, setup, scratch, ctas, out, iters, absn, status, counter, redo, n_redo, st);
-    if (KP == 32) return skb_launch_t<32>(props, K, prm, pm, setup, scratch, ctas, out, iters, absn, status, counter, redo, n_redo, st);
-    return skb_launch_t<64>(props, K, prm, pm, setup, scratch, ctas, out, iters, absn, status, counter, redo, n_redo, st);
+#define SKB_GO(KPV, FULLV) \
+    return skb_launch_t<KPV, FULLV>(props, K, prm, pm, slot_cap, setup, scratch, ctas, out, iters, absn, status, \
+                                    counter, redo, n_redo, st)
+    if (KP == 16) { if (K == 16) SKB_GO(16, true); SKB_GO(16, false); }
+    if (KP == 32) { if (K == 32) SKB_GO(32, true); SKB_GO(32, false); }
+    if (K == 64) SKB_GO(64, true);
+    SKB_GO(64, false);
+#undef SKB_GO
 }
 
 }  // namespace pilot

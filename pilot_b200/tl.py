@@ -46,7 +46,9 @@ def extract_data_anno_scRNA_from_h5ad(adata, emb_matrix="PCA", clusters_col="cel
     global path_to_results
     data = adata.obsm[emb_matrix]
     cols = ["PCA_" + str(i) for i in range(1, adata.obsm[emb_matrix].shape[1] + 1)]
-    data = pd.DataFrame(data, columns=cols)
+    # copy=False: share the embedding's memory like pandas 2.0.x (the version the reference pins,
+    # setup.py:21) does for ndarray input, instead of pandas >= 3's transposing 200 MB copy
+    data = pd.DataFrame(data, columns=cols, copy=False)
     data = data.reset_index(drop=True)
     annot = adata.obs[[clusters_col, sample_col, status]]
     annot.columns = ["cell_type", "sampleID", "status"]
@@ -60,7 +62,7 @@ def extract_data_anno_pathomics_from_h5ad(adata, var_names=[], clusters_col="Cel
     """(data, annot) DataFrames from adata[:, var_names].X and three obs columns."""
     global path_to_results
     data = adata[:, var_names].X
-    data = pd.DataFrame(data, columns=var_names)
+    data = pd.DataFrame(data, columns=var_names, copy=False)
     data = data.reset_index(drop=True)
     annot = adata.obs[[clusters_col, sample_col, status]]
     annot.columns = ["cell_type", "sampleID", "status"]
@@ -141,7 +143,11 @@ def _embedding_to_device(data) -> torch.Tensor:
     X = data.to_numpy() if isinstance(data, pd.DataFrame) else np.asarray(data)
     if X.dtype not in (np.float32, np.float64):
         X = X.astype(np.float64)  # pandas' nanmedian promotes non-float input to float64
-    return _to_device(np.ascontiguousarray(X))
+    if X.ndim != 2:
+        raise ValueError("embedding must be 2-dimensional")
+    if not X.flags.c_contiguous:
+        X = np.ascontiguousarray(X)
+    return _to_device(X)
 
 
 def _props_dict(samples, props_host: np.ndarray) -> Dict[object, np.ndarray]:
@@ -275,7 +281,8 @@ def wasserstein_distance(adata, emb_matrix="X_PCA", clusters_col="cell_types", s
     adata.uns["annot"] = annot
 
     lab = _Labels(annot, "cell_type", "sampleID")
-    X_dev = _embedding_to_device(data)
+    # stage the embedding straight from the caller's array (no detour through the DataFrame)
+    X_dev = _embedding_to_device(adata.obsm[emb_matrix] if data_type == "scRNA" else data)
     props, counts = lab.proportions(regulizer, normalization)
     cost, cost_norm = _cost_device(lab, X_dev, metric)
     props_h = props.cpu().numpy()
@@ -298,4 +305,4 @@ def wasserstein_distance(adata, emb_matrix="X_PCA", clusters_col="cell_types", s
             "scanpy + leidenalg), which is outside the patient-distance hot path (SURVEY.md 8f #4); call "
             "pilotpy.tl.Clustering / Sil_computing on adata.uns['EMD'] instead.")
     # first status per sample, via the first-appearance cell index the histogram kernel produced
-    adata.uns["real_labels"] = list(annot["status"].to_numpy()[lab.first_smp])
+    adata.uns["real_labels"] = list(annot["status"].iloc[lab.first_smp])
