@@ -244,10 +244,10 @@ class DeviceStep:
 
 
 # kernel launches of ONE DeviceStep.run() (my kernels only; memsets and torch's index_select excluded):
-# hist_init + hist (2), colsum + finalize (2), median 4 x (hist + scan) + final (9), cdist prep/pair/norm (3),
+# hist_init + hist (2), prior + finalize (2), median count + pivot + stream + finish (4), cdist prep/pair/norm (3),
 # sinkhorn setup + batched + reference-form redo (3) or emd (1), unpack (1)
 def launches_per_step(reg):
-    return 2 + 2 + 9 + 3 + (3 if reg is not None else 1) + 1
+    return 2 + 2 + 4 + 3 + (3 if reg is not None else 1) + 1
 
 
 def pair_kernel_slices(peak_fp64):

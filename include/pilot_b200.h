@@ -95,14 +95,15 @@ int pilot_hist(const int32_t *ct_code, const int32_t *smp_code, int64_t n_cells,
  * counts_raw is pilot_hist's table (S_raw x K_raw, raw-code order); perm_s[S] /
  * perm_k[K] (device int32, NULL = identity) list the raw codes in order of first
  * appearance, so props[s*K+k] and counts_out[s*K+k] (optional) come out in the
- * reference's `.unique()` order.  normalization==0 copies the raw counts
- * (Trajectory.py:425).
+ * reference's `.unique()` order.  prior_out[K+1] receives the Dirichlet prior
+ * n_k/(N-1)*regulizer and, last, its sequential sum.  normalization==0 copies
+ * the raw counts (Trajectory.py:425).
  */
 int pilot_props_finalize(const int64_t *counts_raw, int K_raw, int S_raw,
                          const int32_t *perm_k, const int32_t *perm_s, int K,
                          int S, int64_t n_cells, double regulizer,
                          int normalization, double *props, int64_t *counts_out,
-                         void *stream);
+                         double *prior_out, void *stream);
 
 /*
  * (2a) Per-type, per-dimension MEDIAN of the embedding rows in the input dtype
@@ -119,7 +120,8 @@ int pilot_centroid_median(const void *X, int dtype, int64_t n_cells, int D,
 /*
  * (2b) K x K distance matrix between centroids -- replaces
  * squareform(pdist(centroids, metric)), Trajectory.py:468-469.  Also writes
- * cost_norm = cost / max(cost) (Trajectory.py:101) and *cost_max.
+ * cost_norm = cost / max(cost) (Trajectory.py:101) and *cost_max; cost_norm
+ * (required) doubles as scratch while the pairs are computed.
  */
 int pilot_cdist(const double *centroids_f64, int K, int D, int metric,
                 double *cost, double *cost_norm, double *cost_max, void *stream);

@@ -67,7 +67,7 @@ def lib():
     L.pilot_hist.restype = i32
     L.pilot_hist.argtypes = [vp, vp, i64, i32, i32, vp, vp, vp, vp]
     L.pilot_props_finalize.restype = i32
-    L.pilot_props_finalize.argtypes = [vp, i32, i32, vp, vp, i32, i32, i64, dbl, i32, vp, vp, vp]
+    L.pilot_props_finalize.argtypes = [vp, i32, i32, vp, vp, i32, i32, i64, dbl, i32, vp, vp, vp, vp]
     L.pilot_centroid_median.restype = i32
     L.pilot_centroid_median.argtypes = [vp, i32, i64, i32, i64, vp, i32, vp, vp, vp, sz, vp]
     L.pilot_cdist.restype = i32

@@ -48,7 +48,7 @@ int make_pair_map(const pilot_pair_range *r, int S, PairMap *pm)
     return 0;
 }
 
-size_t median_ws_bytes(int K, int D);
+size_t median_ws_bytes(long long n, int K, int D);
 size_t sinkhorn_ws_bytes(int K);
 
 }  // namespace pilot
@@ -57,9 +57,9 @@ extern "C" {
 
 size_t pilot_workspace_bytes(int kind, int64_t n, int K, int S, int D)
 {
-    (void)n; (void)S;
+    (void)S;
     switch (kind) {
-    case PILOT_WS_MEDIAN:   return pilot::median_ws_bytes(K, D);
+    case PILOT_WS_MEDIAN:   return pilot::median_ws_bytes(n, K, D);
     case PILOT_WS_SINKHORN: return pilot::sinkhorn_ws_bytes(K);
     case PILOT_WS_EMD:      return 256;
     default:                return 0;

@@ -114,19 +114,23 @@ extern "C" int pilot_cdist(const double *centroids_f64, int K, int D, int metric
     PILOT_CHECK_ARG(metric >= PILOT_METRIC_COSINE && metric <= PILOT_METRIC_CORRELATION,
                     "pilot_cdist: unsupported metric id %d", metric);
     PILOT_CHECK_ARG(K <= 4096, "pilot_cdist: K=%d too large", K);
+    PILOT_CHECK_ARG(cost_norm != nullptr, "pilot_cdist: cost_norm is required (it doubles as scratch)");
     cudaStream_t st = (cudaStream_t)stream;
-    double *scratch = nullptr;
-    PILOT_CUDA(cudaMallocAsync((void **)&scratch, sizeof(double) * 2 * K, st));
+    if (K == 1) {
+        // a single centroid: cost = [[0]]; cost / cost.max() = 0/0 = NaN like NumPy
+        PILOT_CUDA(cudaMemsetAsync(cost, 0, sizeof(double), st));
+        cdist_norm_kernel<<<1, 32, 0, st>>>(cost, 1, cost_norm, cost_max);
+        PILOT_LAUNCH_CHECK();
+        return 0;
+    }
+    double *scratch = cost_norm;  // norms[K], means[K]: K*K >= 2K for K >= 2
     cdist_prep_kernel<<<(K + 127) / 128, 128, 0, st>>>(centroids_f64, K, D, metric, scratch, scratch + K);
     PILOT_LAUNCH_CHECK();
     const long long n = (long long)K * K;
     cdist_pair_kernel<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(centroids_f64, K, D, metric, scratch,
                                                                   scratch + K, cost);
     PILOT_LAUNCH_CHECK();
-    if (cost_norm || cost_max) {
-        cdist_norm_kernel<<<1, 1024, 0, st>>>(cost, K, cost_norm, cost_max);
-        PILOT_LAUNCH_CHECK();
-    }
-    PILOT_CUDA(cudaFreeAsync(scratch, st));
+    cdist_norm_kernel<<<1, 1024, 0, st>>>(cost, K, cost_norm, cost_max);
+    PILOT_LAUNCH_CHECK();
     return 0;
 }

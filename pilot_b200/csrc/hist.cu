@@ -103,25 +103,34 @@ __global__ void hist_init_kernel(unsigned long long *counts, long long sk, unsig
     if (i < S) first_smp[i] = n;
 }
 
-// Column sums n_k of the (permuted) count table: CTA b reduces a slab of rows in
-// shared memory and writes partial[b][k]; integers, so any order is exact.
-__global__ void props_colsum_kernel(const long long *__restrict__ counts_raw, int K_raw,
-                                    const int *__restrict__ perm_s, const int *__restrict__ perm_k,
-                                    int K, int S, int rows_per_cta, unsigned long long *__restrict__ partial)
+// prior_k = n_k/(N-1)*regulizer and its sequential sum (Trajectory.py:405-409, :430).  One CTA of
+// K x R threads: thread (r, k) adds the rows s = r (mod R) of column k (integers: any order is
+// exact), a shared-memory pass folds the R partials, thread 0 takes the left-to-right FP64 sum.
+__global__ void props_prior_kernel(const long long *__restrict__ counts_raw, int K_raw,
+                                   const int *__restrict__ perm_s, const int *__restrict__ perm_k,
+                                   int K, int S, int R, long long n_cells, double regulizer,
+                                   double *__restrict__ prior)
 {
-    extern __shared__ unsigned long long s_nk[];
-    for (int k = threadIdx.x; k < K; k += blockDim.x) s_nk[k] = 0ULL;
-    __syncthreads();
-    const int r0 = blockIdx.x * rows_per_cta;
-    const int r1 = min(S, r0 + rows_per_cta);
-    for (long long e = (long long)r0 * K + threadIdx.x; e < (long long)r1 * K; e += blockDim.x) {
-        const int s = (int)(e / K), k = (int)(e - (long long)s * K);
-        const int sr = perm_s ? perm_s[s] : s, kr = perm_k ? perm_k[k] : k;
-        const long long c = counts_raw[(long long)sr * K_raw + kr];
-        if (c) atomicAdd(&s_nk[k], (unsigned long long)c);
+    extern __shared__ unsigned long long s_part[];  // R x K
+    const int k = threadIdx.x % K, r = threadIdx.x / K;
+    if (r < R) {
+        const int kr = perm_k ? perm_k[k] : k;
+        unsigned long long acc = 0;
+        for (int s = r; s < S; s += R) acc += (unsigned long long)counts_raw[(long long)(perm_s ? perm_s[s] : s) * K_raw + kr];
+        s_part[r * K + k] = acc;
     }
     __syncthreads();
-    for (int k = threadIdx.x; k < K; k += blockDim.x) partial[(long long)blockIdx.x * K + k] = s_nk[k];
+    if (threadIdx.x < K) {
+        unsigned long long nk = 0;
+        for (int q = 0; q < R; ++q) nk += s_part[q * K + threadIdx.x];
+        prior[threadIdx.x] = __dmul_rn(__ddiv_rn((double)nk, (double)(n_cells - 1)), regulizer);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double sp = 0.0;
+        for (int q = 0; q < K; ++q) sp = __dadd_rn(sp, prior[q]);
+        prior[K] = sp;
+    }
 }
 
 // prior_k = n_k/(N-1)*regulizer (Trajectory.py:405-409); every FP sum is a sequential
@@ -129,22 +138,11 @@ __global__ void props_colsum_kernel(const long long *__restrict__ counts_raw, in
 // round-to-nearest intrinsics so nvcc cannot contract into FMA.  One thread per sample row.
 __global__ void props_finalize_kernel(const long long *__restrict__ counts_raw, int K_raw,
                                       const int *__restrict__ perm_s, const int *__restrict__ perm_k,
-                                      int K, int S, long long n_cells, double regulizer, int normalization,
-                                      const unsigned long long *__restrict__ partial, int n_partial,
+                                      int K, int S, int normalization, const double *__restrict__ prior,
                                       double *__restrict__ props, long long *__restrict__ counts_out)
 {
     extern __shared__ double s_prior[];  // K + 1
-    for (int k = threadIdx.x; k < K; k += blockDim.x) {
-        unsigned long long nk = 0;
-        for (int b = 0; b < n_partial; ++b) nk += partial[(long long)b * K + k];
-        s_prior[k] = __dmul_rn(__ddiv_rn((double)nk, (double)(n_cells - 1)), regulizer);
-    }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        double sp = 0.0;
-        for (int k = 0; k < K; ++k) sp = __dadd_rn(sp, s_prior[k]);
-        s_prior[K] = sp;
-    }
+    for (int k = threadIdx.x; k <= K; k += blockDim.x) s_prior[k] = prior[k];
     __syncthreads();
     const double sp = s_prior[K];
     const int s = blockIdx.x * blockDim.x + threadIdx.x;
@@ -216,25 +214,24 @@ extern "C" int pilot_hist(const int32_t *ct_code, const int32_t *smp_code, int64
 
 extern "C" int pilot_props_finalize(const int64_t *counts_raw, int K_raw, int S_raw, const int32_t *perm_k,
                                     const int32_t *perm_s, int K, int S, int64_t n_cells, double regulizer,
-                                    int normalization, double *props, int64_t *counts_out, void *stream)
+                                    int normalization, double *props, int64_t *counts_out, double *prior_out,
+                                    void *stream)
 {
     using namespace pilot;
-    PILOT_CHECK_ARG(K >= 1 && S >= 1 && counts_raw && props, "pilot_props_finalize: bad argument");
+    PILOT_CHECK_ARG(K >= 1 && S >= 1 && counts_raw && props && prior_out, "pilot_props_finalize: bad argument");
     PILOT_CHECK_ARG(K <= K_raw && S <= S_raw, "pilot_props_finalize: K=%d S=%d exceed raw dims %d %d", K, S, K_raw, S_raw);
-    PILOT_CHECK_ARG((size_t)(K + 1) * sizeof(double) <= 48 * 1024, "pilot_props_finalize: K=%d too large", K);
+    PILOT_CHECK_ARG(K <= 1024, "pilot_props_finalize: K=%d too large (max 1024)", K);
     cudaStream_t st = (cudaStream_t)stream;
-    const int n_partial = S < 64 ? 1 : 64;
-    const int rows_per_cta = (S + n_partial - 1) / n_partial;
-    unsigned long long *partial = nullptr;
-    PILOT_CUDA(cudaMallocAsync((void **)&partial, (size_t)n_partial * K * sizeof(unsigned long long), st));
-    props_colsum_kernel<<<n_partial, 256, K * sizeof(unsigned long long), st>>>(
-        (const long long *)counts_raw, K_raw, perm_s, perm_k, K, S, rows_per_cta, partial);
+    int R = 1024 / K;
+    if (R > S) R = S;
+    if (R < 1) R = 1;
+    props_prior_kernel<<<1, K * R, (size_t)R * K * sizeof(unsigned long long), st>>>(
+        (const long long *)counts_raw, K_raw, perm_s, perm_k, K, S, R, n_cells, regulizer, prior_out);
     PILOT_LAUNCH_CHECK();
     const int th = 128;
     props_finalize_kernel<<<(S + th - 1) / th, th, (K + 1) * sizeof(double), st>>>(
-        (const long long *)counts_raw, K_raw, perm_s, perm_k, K, S, n_cells, regulizer, normalization,
-        partial, n_partial, props, (long long *)counts_out);
+        (const long long *)counts_raw, K_raw, perm_s, perm_k, K, S, normalization, prior_out, props,
+        (long long *)counts_out);
     PILOT_LAUNCH_CHECK();
-    PILOT_CUDA(cudaFreeAsync(partial, st));
     return 0;
 }

@@ -85,9 +85,10 @@ def props_finalize(counts_raw: torch.Tensor, perm_k: Optional[torch.Tensor], per
         assert p is None or (p.dtype == torch.int32 and p.is_cuda and p.is_contiguous())
     props = torch.empty((S, K), dtype=torch.float64, device=counts_raw.device)
     counts = torch.empty((S, K), dtype=torch.int64, device=counts_raw.device)
+    prior = torch.empty((K + 1,), dtype=torch.float64, device=counts_raw.device)
     check(lib().pilot_props_finalize(_ptr(counts_raw), K_raw, S_raw, _ptr(perm_k), _ptr(perm_s), K, S, n_cells,
                                      float(regulizer), 1 if normalization else 0, _ptr(props), _ptr(counts),
-                                     _stream()), "pilot_props_finalize")
+                                     _ptr(prior), _stream()), "pilot_props_finalize")
     return props, counts
 
 
@@ -110,6 +111,15 @@ def centroid_median(X: torch.Tensor, ct_code: torch.Tensor, K: int) -> Tuple[tor
     check(lib().pilot_centroid_median(_ptr(X), dt, n, D, X.stride(0), _ptr(ct_code), K, _ptr(cent), _ptr(cent64),
                                       _ptr(ws), ws.numel(), _stream()), "pilot_centroid_median")
     return cent, cent64
+
+
+def median_fallbacks(K: int, D: int, device=None) -> int:
+    """Diagnostic: how many (type, dim) pairs of the LAST centroid_median call on this stream took
+    the exact full-column fallback of the streaming path (reads the workspace; synchronises)."""
+    device = device or torch.device("cuda", torch.cuda.current_device())
+    ws = _workspace(1, device)
+    off = ((K * 8 + 8 + 255) // 256) * 256 + K * D * 32 * 4  # after type_cnt/cand_total and the 32 (MED_G) sub-list counters
+    return int(ws[off:off + 4].view(torch.int32).item())
 
 
 def cdist(cent64: torch.Tensor, metric: str = "cosine") -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:

@@ -66,6 +66,45 @@ def test_centroid_median_bit_exact(dtype, n, K, D):
     np.testing.assert_array_equal(cent64.cpu().numpy(), want.astype(np.float64))
 
 
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+@pytest.mark.parametrize("case", ["gauss", "duplicates", "nan", "skewed_types", "adversarial_sample"])
+def test_centroid_median_streaming_path(dtype, case):
+    """n >= 64K and D >= 32 take the sampled-pivot single-pass path; results must stay exact,
+    including when the sample misleads the pivots (exact in-kernel fallback)."""
+    rng = np.random.default_rng(hash(case) % 1000)
+    n, K, D = 200_000, 10, 50
+    X = rng.normal(size=(n, D)).astype(dtype)
+    code = rng.integers(0, K, size=n).astype(np.int32)
+    if case == "duplicates":
+        X[:, :20] = np.round(X[:, :20], 1)          # ~60 distinct values per column
+        X[:, 20:25] = (rng.random((n, 5)) < 0.7)    # 0/1 features (pathomics-like)
+    elif case == "nan":
+        X[rng.integers(0, n, 5000), rng.integers(0, D, 5000)] = np.nan
+        X[code == 3, 7] = np.nan                    # an all-NaN (type, dim)
+    elif case == "skewed_types":
+        code = np.minimum((rng.exponential(1.2, size=n)).astype(np.int32), K - 1)  # one dominant, some rare
+        code[:K] = np.arange(K)
+    elif case == "adversarial_sample":
+        # sampled rows (blocks of 32 rows every n/1280 rows) all hold 0; the rest is shifted by +5
+        nblocks = -(-min(n, 4096 * K) // 32)
+        bstride = (n // nblocks) // 32 * 32
+        sampled = (np.arange(n) % bstride) < 32
+        X += 5
+        X[sampled] = 0
+    cent, cent64 = ops.centroid_median(dev(X), dev(code), K)
+    fallbacks = ops.median_fallbacks(K, D)
+    if case == "adversarial_sample":
+        assert fallbacks > 0, "the misleading sample must have triggered the exact fallback"
+    elif case == "gauss":
+        assert fallbacks == 0
+    import warnings
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        want = np.stack([np.nanmedian(X[code == k], axis=0) for k in range(K)])
+    np.testing.assert_array_equal(cent.cpu().numpy(), want.astype(dtype))
+    np.testing.assert_array_equal(cent64.cpu().numpy(), want.astype(np.float64))
+
+
 @pytest.mark.parametrize("metric", ["cosine", "euclidean", "sqeuclidean", "cityblock", "chebyshev", "correlation"])
 def test_cdist_matches_scipy(metric):
     rng = np.random.default_rng(4)
