@@ -16,10 +16,16 @@
 //   * potentials:     the cut subtree IS a bitmask -> one predicated add per node
 //   * pricing:        block search over BR rows x all columns (lane = column), shared
 //                     cost matrix in shared memory for all warps of the CTA
-//   * start basis:    diagonal arcs (i,i) with min(a_i,b_i) + north-west corner on the
-//                     residuals -> no artificial arcs, |pi| = O(max cost), ~half the pivots
+//   * compaction:     a cycle has ~7 of the 128 nodes: the cycle nodes are ballot-compacted so
+//                     that ONE lane handles ONE cycle node (ratio test, flow push, re-hanging);
+//                     only cycles longer than 32 nodes take the 4-nodes-per-lane general path
+//   * start basis:    diagonal arcs (i,i) with min(a_i,b_i), then a greedy north-west corner on
+//                     the residuals: the staircase always continues with the CHEAPEST remaining
+//                     column (row) of the current row (column) -> no artificial arcs,
+//                     |pi| = O(max cost), ~4x fewer pivots than the artificial-root start
 // Any exact solver returns the same optimum; parity with the
 // oracle is <1e-12 relative.
+#include <stdlib.h>
 #include "common.cuh"
 
 namespace pilot {
@@ -38,6 +44,8 @@ template <int NW> struct EmdSmem {
     unsigned char parent[N];
     unsigned char tmpc[N];
     unsigned char ord[N];
+    unsigned char size[N];   // popcount of sub[]
+    unsigned char clist[64]; // compacted cycle nodes (bit 7: j-side)
 };
 
 __device__ __forceinline__ int pop_lowest(unsigned (&m)[2], int nw)
@@ -61,18 +69,20 @@ template <int NW>
 __global__ void __launch_bounds__(EMD_WARPS * 32, NW == 2 ? 2 : 3)
 emd_pairs_kernel(const double *__restrict__ props, int K, const double *__restrict__ cost, PairMap pm,
                  long long max_pivots, double *__restrict__ out, int *__restrict__ status,
-                 int *__restrict__ pivots_out, unsigned long long *__restrict__ counter)
+                 int *__restrict__ pivots_out, unsigned long long *__restrict__ counter, int fast_limit)
 {
     using SM = EmdSmem<NW>;
     constexpr int KP = SM::KP, NS = SM::NS;
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    double *sM = reinterpret_cast<double *>(smem_raw);  // KP x KP, row-major, zero padded
-    SM *sw = reinterpret_cast<SM *>(smem_raw + sizeof(double) * KP * KP) + (threadIdx.x >> 5);
+    constexpr int LDM = KP + 1;  // odd row stride: rows AND columns of the cost matrix are conflict free
+    double *sM = reinterpret_cast<double *>(smem_raw);  // KP x LDM, row-major, zero padded
+    SM *sw = reinterpret_cast<SM *>(smem_raw + sizeof(double) * KP * LDM) + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
+    const unsigned lt_mask = (1u << lane) - 1u;
 
     for (int t = threadIdx.x; t < KP * KP; t += blockDim.x) {
         const int i = t / KP, j = t - i * KP;
-        sM[t] = (i < K && j < K) ? cost[i * K + j] : 0.0;
+        sM[i * LDM + j] = (i < K && j < K) ? cost[i * K + j] : 0.0;
     }
     __syncthreads();
 
@@ -136,86 +146,122 @@ emd_pairs_kernel(const double *__restrict__ props, int K, const double *__restri
         }
         __syncwarp();
 
-        // ---------------- start basis: serial north-west corner (lane 0) ----------------
-        int root = 0, chain = 0;
-        if (lane == 0) {
-            int n_ord = 0;
+        // ---------------- start basis: greedy north-west corner (whole warp, uniform state) ----------------
+        int root = 0, chain = 0, n_ord = 0;
+        {
             const bool has_s = any_left(surm, NW), has_d = any_left(defm, NW);
             if (has_s && has_d) {
-                int si = pop_lowest(surm, NW), dj = pop_lowest(defm, NW);
+                // order-preserving 64-bit image of a double (costs may be negative in general)
+                auto okey = [](double v) -> unsigned long long {
+                    const unsigned long long u = (unsigned long long)__double_as_longlong(v);
+                    return (u >> 63) ? ~u : (u | 0x8000000000000000ULL);
+                };
+                // arg-min over the still available rows/columns; lane l looks at l and l + 32
+                auto pick = [&](const unsigned (&avail)[2], bool want_col, int fixed) -> int {
+                    unsigned long long best = ~0ULL;
+                    int bidx = -1;
+#pragma unroll
+                    for (int c = 0; c < NW; ++c) {
+                        const int idx = lane + 32 * c;
+                        if ((avail[c] >> lane) & 1u) {
+                            const double m = want_col ? sM[fixed * LDM + idx] : sM[idx * LDM + fixed];
+                            const unsigned long long kk = okey(m);
+                            if (kk < best) { best = kk; bidx = idx; }
+                        }
+                    }
+                    const unsigned bh = (unsigned)(best >> 32), bl = (unsigned)best;
+                    const unsigned mh = __reduce_min_sync(0xffffffffu, bh);
+                    const unsigned ml = __reduce_min_sync(0xffffffffu, bh == mh ? bl : 0xffffffffu);
+                    const unsigned win = __ballot_sync(0xffffffffu, bidx >= 0 && bh == mh && bl == ml);
+                    return __shfl_sync(0xffffffffu, bidx, __ffs(win) - 1);
+                };
+                int si = pop_lowest(surm, NW);
                 root = si;
+                int dj = pick(defm, true, si);
+                defm[dj >> 5] &= ~(1u << (dj & 31));
                 double rs = sw->amt[si], rd = sw->amt[dj];
                 bool placed_col = false;
                 for (;;) {
                     const double f = fmin(rs, rd);
-                    const double m = sM[si * KP + dj];
-                    if (!placed_col) {
-                        const int x = KP + dj;
-                        sw->parent[x] = (unsigned char)si; sw->flow[x] = f;
-                        sw->pi[x] = sw->pi[si] + m;
-                        sw->ord[n_ord++] = (unsigned char)x;
-                        placed_col = true;
-                    } else {
-                        const int x = si, p = KP + dj;
-                        sw->parent[x] = (unsigned char)p; sw->flow[x] = f;
-                        sw->pi[x] = sw->pi[p] - m;
-                        sw->ord[n_ord++] = (unsigned char)x;
+                    const double m = sM[si * LDM + dj];
+                    if (lane == 0) {
+                        if (!placed_col) {
+                            const int x = KP + dj;
+                            sw->parent[x] = (unsigned char)si; sw->flow[x] = f;
+                            sw->pi[x] = sw->pi[si] + m;
+                            sw->ord[n_ord] = (unsigned char)x;
+                        } else {
+                            const int x = si, p = KP + dj;
+                            sw->parent[x] = (unsigned char)p; sw->flow[x] = f;
+                            sw->pi[x] = sw->pi[p] - m;
+                            sw->ord[n_ord] = (unsigned char)x;
+                        }
                     }
+                    ++n_ord;
+                    placed_col = true;
+                    __syncwarp();
                     const bool last_s = !any_left(surm, NW), last_d = !any_left(defm, NW);
                     if (last_s && last_d) break;
                     if ((rs <= rd && !last_s) || last_d) {
                         rd = fmax(rd - rs, 0.0);
-                        si = pop_lowest(surm, NW);
+                        si = pick(surm, false, dj);        // cheapest remaining row for the current column
+                        surm[si >> 5] &= ~(1u << (si & 31));
                         rs = sw->amt[si];
                     } else {
                         rs = fmax(rs - rd, 0.0);
-                        dj = pop_lowest(defm, NW);
+                        dj = pick(defm, true, si);         // cheapest remaining column for the current row
+                        defm[dj >> 5] &= ~(1u << (dj & 31));
                         rd = sw->amt[dj];
                         placed_col = false;
                     }
                 }
-            } else if (has_s) {
-                // a == b everywhere: chain the (row, leaf col) pairs with zero-flow arcs row_t -> col_{t-1}
-                chain = 1;
-                int prev = pop_lowest(surm, NW);
-                root = prev;
-                sw->pi[KP + prev] = sw->pi[prev] + sM[prev * KP + prev];
-                sw->ord[n_ord++] = (unsigned char)(KP + prev);
-                while (any_left(surm, NW)) {
-                    const int cur = pop_lowest(surm, NW);
-                    sw->parent[cur] = (unsigned char)(KP + prev); sw->flow[cur] = 0.0;
-                    sw->pi[cur] = sw->pi[KP + prev] - sM[cur * KP + prev];
-                    sw->ord[n_ord++] = (unsigned char)cur;
-                    sw->pi[KP + cur] = sw->pi[cur] + sM[cur * KP + cur];
-                    sw->ord[n_ord++] = (unsigned char)(KP + cur);
-                    prev = cur;
-                }
-            } else {
-                // every a_i < b_i (only through rounding): chain (col, leaf row) pairs, arcs row_{t-1} -> col_t
-                chain = 1;
-                int prev = pop_lowest(defm, NW);
-                root = KP + prev;
-                sw->pi[prev] = sw->pi[KP + prev] - sM[prev * KP + prev];
-                sw->ord[n_ord++] = (unsigned char)prev;
-                while (any_left(defm, NW)) {
-                    const int cur = pop_lowest(defm, NW);
-                    sw->parent[KP + cur] = (unsigned char)prev; sw->flow[KP + cur] = 0.0;
-                    sw->pi[KP + cur] = sw->pi[prev] + sM[prev * KP + cur];
-                    sw->ord[n_ord++] = (unsigned char)(KP + cur);
-                    sw->pi[cur] = sw->pi[KP + cur] - sM[cur * KP + cur];
-                    sw->ord[n_ord++] = (unsigned char)cur;
-                    prev = cur;
+            } else if (lane == 0) {
+                if (has_s) {
+                    // a == b everywhere: chain the (row, leaf col) pairs with zero-flow arcs row_t -> col_{t-1}
+                    int prev = pop_lowest(surm, NW);
+                    root = prev;
+                    sw->pi[KP + prev] = sw->pi[prev] + sM[prev * LDM + prev];
+                    sw->ord[n_ord++] = (unsigned char)(KP + prev);
+                    while (any_left(surm, NW)) {
+                        const int cur = pop_lowest(surm, NW);
+                        sw->parent[cur] = (unsigned char)(KP + prev); sw->flow[cur] = 0.0;
+                        sw->pi[cur] = sw->pi[KP + prev] - sM[cur * LDM + prev];
+                        sw->ord[n_ord++] = (unsigned char)cur;
+                        sw->pi[KP + cur] = sw->pi[cur] + sM[cur * LDM + cur];
+                        sw->ord[n_ord++] = (unsigned char)(KP + cur);
+                        prev = cur;
+                    }
+                } else {
+                    // every a_i < b_i (only through rounding): chain (col, leaf row) pairs, arcs row_{t-1} -> col_t
+                    int prev = pop_lowest(defm, NW);
+                    root = KP + prev;
+                    sw->pi[prev] = sw->pi[KP + prev] - sM[prev * LDM + prev];
+                    sw->ord[n_ord++] = (unsigned char)prev;
+                    while (any_left(defm, NW)) {
+                        const int cur = pop_lowest(defm, NW);
+                        sw->parent[KP + cur] = (unsigned char)prev; sw->flow[KP + cur] = 0.0;
+                        sw->pi[KP + cur] = sw->pi[prev] + sM[prev * LDM + cur];
+                        sw->ord[n_ord++] = (unsigned char)(KP + cur);
+                        sw->pi[cur] = sw->pi[KP + cur] - sM[cur * LDM + cur];
+                        sw->ord[n_ord++] = (unsigned char)cur;
+                        prev = cur;
+                    }
                 }
             }
+            if (!(has_s && has_d)) {
+                chain = 1;
+                root = __shfl_sync(0xffffffffu, root, 0);
+                n_ord = __shfl_sync(0xffffffffu, n_ord, 0);
+            }
+            __syncwarp();
             // subtree masks: children were placed after their parents
-            for (int t = n_ord - 1; t >= 0; --t) {
-                const int x = sw->ord[t], p = sw->parent[x];
+            if (lane == 0)
+                for (int t = n_ord - 1; t >= 0; --t) {
+                    const int x = sw->ord[t], p = sw->parent[x];
 #pragma unroll
-                for (int w = 0; w < NS; ++w) sw->sub[p][w] |= sw->sub[x][w];
-            }
+                    for (int w = 0; w < NS; ++w) sw->sub[p][w] |= sw->sub[x][w];
+                }
         }
-        root = __shfl_sync(0xffffffffu, root, 0);
-        chain = __shfl_sync(0xffffffffu, chain, 0);
         __syncwarp();
         if (!chain) {
             // leaf potentials (parents are final now)
@@ -224,13 +270,24 @@ emd_pairs_kernel(const double *__restrict__ props, int K, const double *__restri
                 const int idx = lane + 32 * c;
                 if (valid[c]) {
                     const int r = idx, cn = KP + idx;
-                    const double m = sM[idx * KP + idx];
+                    const double m = sM[idx * LDM + idx];
                     if (sw->parent[cn] == r && av[c] >= bv[c]) sw->pi[cn] = sw->pi[r] + m;
                     else if (sw->parent[r] == cn && !(av[c] >= bv[c])) sw->pi[r] = sw->pi[cn] - m;
                 }
             }
             __syncwarp();
         }
+
+        // subtree sizes (popcount of the masks), kept next to the masks from here on
+#pragma unroll
+        for (int sl_ = 0; sl_ < NS; ++sl_) {
+            const int y = sl_ * 32 + lane;
+            int p = 0;
+#pragma unroll
+            for (int w = 0; w < NS; ++w) p += __popc(sw->sub[y][w]);
+            sw->size[y] = (unsigned char)p;
+        }
+        __syncwarp();
 
         // ---------------- simplex iterations ----------------
         int r0 = 0, npiv = 0, st = PILOT_ST_CONVERGED;
@@ -252,7 +309,7 @@ emd_pairs_kernel(const double *__restrict__ props, int K, const double *__restri
                     const double pr = sw->pi[i];
 #pragma unroll
                     for (int c = 0; c < NW; ++c) {
-                        const double rc = (sM[i * KP + lane + 32 * c] + pr) - pj[c];
+                        const double rc = (sM[i * LDM + lane + 32 * c] + pr) - pj[c];
                         if (valid[c] && rc < brc) { brc = rc; bi = i; bc = c; }
                     }
                 }
@@ -269,7 +326,7 @@ emd_pairs_kernel(const double *__restrict__ props, int K, const double *__restri
                 const int ci = __shfl_sync(0xffffffffu, bi, wl);
                 const int cj = __shfl_sync(0xffffffffu, bc, wl) * 32 + wl;
                 const double rc = -__longlong_as_double((long long)(((unsigned long long)mhi << 32) | mlo));
-                const double sc = fmax(fmax(fabs(sw->pi[ci]), fabs(sw->pi[KP + cj])), fabs(sM[ci * KP + cj]));
+                const double sc = fmax(fmax(fabs(sw->pi[ci]), fabs(sw->pi[KP + cj])), fabs(sM[ci * LDM + cj]));
                 if (rc < -EPS * sc) { ei = ci; ej = cj; erc = rc; break; }
             }
             if (ei < 0) break;  // optimal
@@ -279,6 +336,102 @@ emd_pairs_kernel(const double *__restrict__ props, int K, const double *__restri
             const int jn = KP + ej;
             const int wi = ei >> 5, wj = jn >> 5;
             const unsigned bitI = 1u << (ei & 31), bitJ = 1u << (jn & 31);
+            // compact the cycle nodes: i-side = has i but not j, j-side = has j but not i
+            int ncyc = 0;
+#pragma unroll
+            for (int sl_ = 0; sl_ < NS; ++sl_) {
+                const int y = sl_ * 32 + lane;
+                const unsigned hi_ = sw->sub[y][wi] & bitI, hj_ = sw->sub[y][wj] & bitJ;
+                const bool cI = hi_ && !hj_, cJ = hj_ && !hi_;
+                const unsigned balI = __ballot_sync(0xffffffffu, cI), balJ = __ballot_sync(0xffffffffu, cJ);
+                const int nI = __popc(balI);
+                if (cI) { const int pos = ncyc + __popc(balI & lt_mask); if (pos < 64) sw->clist[pos] = (unsigned char)y; }
+                if (cJ) { const int pos = ncyc + nI + __popc(balJ & lt_mask); if (pos < 64) sw->clist[pos] = (unsigned char)(y | 0x80); }
+                ncyc += nI + __popc(balJ);
+            }
+            __syncwarp();
+            if (ncyc <= fast_limit) {
+                // ---------- one lane per cycle node ----------
+                const bool has = lane < ncyc;
+                const int ye = has ? sw->clist[lane] : 0;
+                const int y = ye & 0x7f;
+                const bool onJ = (ye & 0x80) != 0;
+                const double f = has ? sw->flow[y] : 0.0;
+                const int sz = has ? sw->size[y] : 0;
+                const int par = has ? sw->parent[y] : 0;
+                const bool dec = has && (onJ ? (y >= KP) : (y < KP));  // i-side rows / j-side columns lose flow
+                // ratio test: min flow, ties -> last in cycle order (Cunningham)
+                const unsigned long long fb = dec ? (unsigned long long)__double_as_longlong(f) : ~0ULL;
+                const unsigned od = dec ? (onJ ? (unsigned)(256 + sz) : (unsigned)(256 - sz)) : 0u;
+                const unsigned fh = (unsigned)(fb >> 32), fl_ = (unsigned)fb;
+                const unsigned m1 = __reduce_min_sync(0xffffffffu, fh);
+                const unsigned m2 = __reduce_min_sync(0xffffffffu, fh == m1 ? fl_ : 0xffffffffu);
+                const bool tie = dec && fh == m1 && fl_ == m2;
+                const unsigned m3 = __reduce_max_sync(0xffffffffu, tie ? od : 0u);
+                if (m3 == 0u) { st = PILOT_ST_UNBOUNDED; break; }
+                const int wl = __ffs(__ballot_sync(0xffffffffu, tie && od == m3)) - 1;
+                const int u_out = __shfl_sync(0xffffffffu, y, wl);
+                const int pc_out = __shfl_sync(0xffffffffu, sz, wl);
+                const double delta = __longlong_as_double((long long)(((unsigned long long)m1 << 32) | m2));
+                const bool sideJ = m3 > 256u;
+                const int u_in = sideJ ? jn : ei, v_in = sideJ ? ei : jn;
+                const double sigma = sideJ ? erc : -erc;
+                unsigned T2[NS];
+#pragma unroll
+                for (int w = 0; w < NS; ++w) T2[w] = sw->sub[u_out][w];
+                // phase A: push delta round the cycle; stem children announce themselves
+                const double fU = dec ? f - delta : f + delta;
+                const bool same = has && (onJ == sideJ);
+                const bool stem = same && sz <= pc_out;
+                if (has) sw->flow[y] = fU;
+                if (stem && y != u_out) sw->tmpc[par] = (unsigned char)y;
+                __syncwarp();
+                // phase B: stem nodes fetch their stem child's (updated) flow, old subtree and size
+                int ch = 0, csz = 0;
+                double cf = 0.0;
+                unsigned csub[NS];
+#pragma unroll
+                for (int w = 0; w < NS; ++w) csub[w] = 0u;
+                if (stem && y != u_in) {
+                    ch = sw->tmpc[y];
+                    cf = sw->flow[ch];
+                    csz = sw->size[ch];
+#pragma unroll
+                    for (int w = 0; w < NS; ++w) csub[w] = sw->sub[ch][w];
+                }
+                __syncwarp();
+                // phase C: rewrite parent / flow / sub / size of the cycle nodes
+                if (stem) {
+                    if (y == u_in) {
+                        sw->parent[y] = (unsigned char)v_in;
+                        sw->flow[y] = delta;
+                        sw->size[y] = (unsigned char)pc_out;
+#pragma unroll
+                        for (int w = 0; w < NS; ++w) sw->sub[y][w] = T2[w];
+                    } else {
+                        sw->parent[y] = (unsigned char)ch;
+                        sw->flow[y] = cf;
+                        sw->size[y] = (unsigned char)(pc_out - csz);
+#pragma unroll
+                        for (int w = 0; w < NS; ++w) sw->sub[y][w] = T2[w] & ~csub[w];
+                    }
+                } else if (same) {  // above u_out on its side: loses the cut subtree
+                    sw->size[y] = (unsigned char)(sz - pc_out);
+#pragma unroll
+                    for (int w = 0; w < NS; ++w) sw->sub[y][w] &= ~T2[w];
+                } else if (has) {   // the other side: v_in and its ancestors below the join gain it
+                    sw->size[y] = (unsigned char)(sz + pc_out);
+#pragma unroll
+                    for (int w = 0; w < NS; ++w) sw->sub[y][w] |= T2[w];
+                }
+                // potentials of the re-hung subtree
+#pragma unroll
+                for (int sl_ = 0; sl_ < NS; ++sl_)
+                    if ((T2[sl_] >> lane) & 1u) sw->pi[sl_ * 32 + lane] += sigma;
+                __syncwarp();
+                continue;
+            }
+            // ---------- general path (cycles longer than 32 nodes): 4 nodes per lane ----------
             unsigned sb[NS][NS];
             int pc[NS];
             bool isI[NS], isJ[NS];
@@ -402,6 +555,16 @@ emd_pairs_kernel(const double *__restrict__ props, int K, const double *__restri
                 if (inT2) sw->pi[y] += sigma;
             }
             __syncwarp();
+            // keep the stored subtree sizes in step with the masks
+#pragma unroll
+            for (int s = 0; s < NS; ++s) {
+                const int y = s * 32 + lane;
+                int p = 0;
+#pragma unroll
+                for (int w = 0; w < NS; ++w) p += __popc(sw->sub[y][w]);
+                sw->size[y] = (unsigned char)p;
+            }
+            __syncwarp();
         }
 
         // ---------------- objective: sum of flow * cost over the basic arcs ----------------
@@ -411,7 +574,7 @@ emd_pairs_kernel(const double *__restrict__ props, int K, const double *__restri
             const int y = s * 32 + lane;
             const int p = sw->parent[y];
             if (p != 255 && y != root) {
-                const double m = (s < NW) ? sM[y * KP + (p - KP)] : sM[p * KP + (y - KP)];
+                const double m = (s < NW) ? sM[y * LDM + (p - KP)] : sM[p * LDM + (y - KP)];
                 acc += sw->flow[y] * m;
             }
         }
@@ -430,7 +593,7 @@ static int emd_launch(const double *props, int K, const double *cost, const Pair
                       double *out, int *status, int *pivots, unsigned long long *counter, cudaStream_t st)
 {
     using SM = EmdSmem<NW>;
-    const size_t smem = sizeof(double) * SM::KP * SM::KP + sizeof(SM) * EMD_WARPS;
+    const size_t smem = sizeof(double) * SM::KP * (SM::KP + 1) + sizeof(SM) * EMD_WARPS;
     PILOT_CUDA(cudaFuncSetAttribute(emd_pairs_kernel<NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = 1;
     PILOT_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, emd_pairs_kernel<NW>, EMD_WARPS * 32, smem));
@@ -439,8 +602,15 @@ static int emd_launch(const double *props, int K, const double *cost, const Pair
     const long long need = (pm.n_local + EMD_WARPS - 1) / EMD_WARPS;
     if (ctas > need) ctas = need;
     if (ctas < 1) ctas = 1;
+    // PILOT_EMD_FAST_LIMIT (0..32, tests only): longest cycle handled by the one-lane-per-node path
+    int fast_limit = 32;
+    if (const char *e = getenv("PILOT_EMD_FAST_LIMIT")) {
+        fast_limit = atoi(e);
+        if (fast_limit < 0) fast_limit = 0;
+        if (fast_limit > 32) fast_limit = 32;
+    }
     emd_pairs_kernel<NW><<<(unsigned)ctas, EMD_WARPS * 32, smem, st>>>(props, K, cost, pm, max_pivots, out, status,
-                                                                     pivots, counter);
+                                                                     pivots, counter, fast_limit);
     PILOT_LAUNCH_CHECK();
     return 0;
 }

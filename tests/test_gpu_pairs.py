@@ -36,6 +36,18 @@ def test_emd_pairs_match_oracle(K):
     assert np.abs(np.diag(got)).max() <= 1e-15
 
 
+@pytest.mark.parametrize("limit", ["0", "3"])
+def test_emd_general_pivot_path(limit, monkeypatch):
+    """Cycles longer than the one-lane-per-node path can take (forced here) use the general path."""
+    monkeypatch.setenv("PILOT_EMD_FAST_LIMIT", limit)
+    for K in (10, 40, 64):
+        S = 12
+        P, M = synth.make_pairs(S, K, seed=500 + K)
+        out, status, piv = ops.emd_pairs(dev(P), dev(M), ops.make_range(S * S, _lib.PAIRS_FULL), want_info=True)
+        assert (status.cpu().numpy() == 0).all()
+        np.testing.assert_allclose(out.cpu().numpy().reshape(S, S), oracle_emd_matrix(P, M), rtol=EMD_RTOL, atol=1e-15)
+
+
 def test_emd_degenerate_inputs():
     K = 12
     P, M = synth.make_pairs(6, K, seed=1)
