@@ -42,8 +42,7 @@ template <int NW> struct EmdSmem {
     double pi[N];
     double amt[KP];
     unsigned char parent[N];
-    unsigned char tmpc[N];
-    unsigned char ord[N];
+    unsigned char tmpc[N];   // stem-child scatter during pivots; placement order (`ord`) during the start basis
     unsigned char size[N];   // popcount of sub[]
     unsigned char clist[64]; // compacted cycle nodes (bit 7: j-side)
 };
@@ -189,12 +188,12 @@ emd_pairs_kernel(const double *__restrict__ props, int K, const double *__restri
                             const int x = KP + dj;
                             sw->parent[x] = (unsigned char)si; sw->flow[x] = f;
                             sw->pi[x] = sw->pi[si] + m;
-                            sw->ord[n_ord] = (unsigned char)x;
+                            sw->tmpc[n_ord] = (unsigned char)x;
                         } else {
                             const int x = si, p = KP + dj;
                             sw->parent[x] = (unsigned char)p; sw->flow[x] = f;
                             sw->pi[x] = sw->pi[p] - m;
-                            sw->ord[n_ord] = (unsigned char)x;
+                            sw->tmpc[n_ord] = (unsigned char)x;
                         }
                     }
                     ++n_ord;
@@ -221,14 +220,14 @@ emd_pairs_kernel(const double *__restrict__ props, int K, const double *__restri
                     int prev = pop_lowest(surm, NW);
                     root = prev;
                     sw->pi[KP + prev] = sw->pi[prev] + sM[prev * LDM + prev];
-                    sw->ord[n_ord++] = (unsigned char)(KP + prev);
+                    sw->tmpc[n_ord++] = (unsigned char)(KP + prev);
                     while (any_left(surm, NW)) {
                         const int cur = pop_lowest(surm, NW);
                         sw->parent[cur] = (unsigned char)(KP + prev); sw->flow[cur] = 0.0;
                         sw->pi[cur] = sw->pi[KP + prev] - sM[cur * LDM + prev];
-                        sw->ord[n_ord++] = (unsigned char)cur;
+                        sw->tmpc[n_ord++] = (unsigned char)cur;
                         sw->pi[KP + cur] = sw->pi[cur] + sM[cur * LDM + cur];
-                        sw->ord[n_ord++] = (unsigned char)(KP + cur);
+                        sw->tmpc[n_ord++] = (unsigned char)(KP + cur);
                         prev = cur;
                     }
                 } else {
@@ -236,14 +235,14 @@ emd_pairs_kernel(const double *__restrict__ props, int K, const double *__restri
                     int prev = pop_lowest(defm, NW);
                     root = KP + prev;
                     sw->pi[prev] = sw->pi[KP + prev] - sM[prev * LDM + prev];
-                    sw->ord[n_ord++] = (unsigned char)prev;
+                    sw->tmpc[n_ord++] = (unsigned char)prev;
                     while (any_left(defm, NW)) {
                         const int cur = pop_lowest(defm, NW);
                         sw->parent[KP + cur] = (unsigned char)prev; sw->flow[KP + cur] = 0.0;
                         sw->pi[KP + cur] = sw->pi[prev] + sM[prev * LDM + cur];
-                        sw->ord[n_ord++] = (unsigned char)(KP + cur);
+                        sw->tmpc[n_ord++] = (unsigned char)(KP + cur);
                         sw->pi[cur] = sw->pi[KP + cur] - sM[cur * LDM + cur];
-                        sw->ord[n_ord++] = (unsigned char)cur;
+                        sw->tmpc[n_ord++] = (unsigned char)cur;
                         prev = cur;
                     }
                 }
@@ -257,7 +256,7 @@ emd_pairs_kernel(const double *__restrict__ props, int K, const double *__restri
             // subtree masks: children were placed after their parents
             if (lane == 0)
                 for (int t = n_ord - 1; t >= 0; --t) {
-                    const int x = sw->ord[t], p = sw->parent[x];
+                    const int x = sw->tmpc[t], p = sw->parent[x];
 #pragma unroll
                     for (int w = 0; w < NS; ++w) sw->sub[p][w] |= sw->sub[x][w];
                 }
