@@ -358,12 +358,38 @@ def run_b200(args):
     elt = X.dtype.itemsize
     alg_bytes = {"hist": n * 8 + s * k * 8, "median": n * d * elt + n * 4 + k * d * elt}
     dominant = max(stage_ms, key=stage_ms.get)
-    roofline = None
+    # FP64 pipe peaks are not in MEASURED_PEAKS.json: measure them here (DFMA, FFMA, FP64 mma.sync)
+    peaks = {"fp64_fma_tflops": ops.pipe_peak(0), "fp32_fma_tflops": ops.pipe_peak(1),
+             "fp64_dmma_tflops": ops.pipe_peak(2)}
     if dominant in alg_bytes:
         ach = alg_bytes[dominant] / (stage_ms[dominant] * 1e-3) / 1e9
         roofline = {"kernel": dominant, "bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s",
-                    "frac": ach / hbm_peak, "traffic": None, "peak_source": peak_kind,
+                    "frac": ach / hbm_peak, "traffic": None, "peak_source": peak_kind + " (MEASURED_PEAKS.json hbm_gbs)",
                     "algorithmic_bytes": alg_bytes[dominant], "ms": stage_ms[dominant]}
+    else:
+        # the all-pairs stage dominates: algorithmic flops = sum over this rank's problems of iters * 4 K^2
+        # (SURVEY 8d); its matvecs run on the FP64 tensor path (mma.sync m8n8k4 f64)
+        from pilot_b200 import _lib, pairs as _pairs
+        if reg is not None:
+            total = s * s
+            rng = _lib.PairRange(total=total, block=_pairs.choose_block(total, world), nranks=world, rank=rank,
+                                 mode=_lib.PAIRS_FULL, reserved=0)
+            _, it, _, _ = ops.sinkhorn_pairs(props, cost / cost.max(), reg, rng, want_info=True)
+            flops = float(it.sum().item()) * 4.0 * k * k
+            mean_iters = float(it.float().mean().item())
+            max_iters = int(it.max().item())
+        else:
+            flops, mean_iters, max_iters = float("nan"), None, None
+        ach = flops / (stage_ms[dominant] * 1e-3) / 1e12
+        roofline = {"kernel": "sinkhorn_batched_kernel (all-pairs stage incl. setup/unpack)", "bound": "tensor",
+                    "achieved": ach, "peak": peaks["fp64_dmma_tflops"], "unit": "TFLOP/s",
+                    "frac": ach / peaks["fp64_dmma_tflops"], "traffic": None,
+                    "peak_source": "FP64 mma.sync peak measured in this run by pilot_pipe_peak (MEASURED_PEAKS.json "
+                                   "holds only bf16 and HBM peaks)",
+                    "algorithmic_flops": flops, "mean_iters": mean_iters, "max_iters": max_iters,
+                    "ms": stage_ms[dominant],
+                    "note": "C2 is 10^4 problems of up to 1000 dependent iterations: latency-bound by construction; "
+                            "see kernels.sinkhorn_c5_slice for the throughput-bound figure"}
 
     # ---------------- end to end through the public API ----------------
     pinned = torch.empty(X.shape, dtype=torch.float32 if X.dtype == np.float32 else torch.float64, pin_memory=True)
@@ -413,20 +439,13 @@ def run_b200(args):
             "gpu_launches": launches_per_step(reg) * args.steps,
             "stage_ms": stage_ms, "roofline": roofline}
 
+    line["pipe_peaks"] = peaks
     if n_gpus == 1:
-        # pipe peaks (roofline denominators the driver does not measure) and the pair kernels at C5 shape
-        peaks = {"fp64_fma_tflops": ops.pipe_peak(0), "fp32_fma_tflops": ops.pipe_peak(1),
-                 "fp64_dmma_tflops": ops.pipe_peak(2)}
-        line["pipe_peaks"] = peaks
+        # the two pair kernels alone at the C5 shape (K = 64, S = 20 000)
         try:
             line["kernels"] = pair_kernel_slices(peaks["fp64_fma_tflops"])
         except Exception as exc:  # keep the headline line even if the extra slices fail
             line["kernels"] = {"error": repr(exc)}
-        if roofline is None:
-            # dominant stage is the pair kernel: FP64 FMA pipe bound
-            iters = None
-            line["roofline"] = {"kernel": dominant, "bound": "fp64-fma", "achieved": None, "peak": peaks["fp64_fma_tflops"],
-                                "unit": "TFLOP/s", "frac": None, "traffic": None, "ms": stage_ms[dominant]}
         cb = cpu_reference_step(X, obs, reg, 4)
         line["cpu_baseline"] = {
             "value": cb["problems_per_s"], "unit": UNIT, "cores": 1, "kind": cb["kind"],

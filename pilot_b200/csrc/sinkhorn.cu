@@ -54,17 +54,18 @@ extern "C" int pilot_sinkhorn_pairs(const double *props, int S, int K, const dou
     ws.setup = (double *)(p + 256);
     ws.scratch = (double *)(p + 256 + skb_setup_bytes(KP));
     ws.redo = (long long *)(p + 256 + skb_setup_bytes(KP) + skb_scratch_bytes(KP, sm_count()));
-    // persistent grid: one CTA per SM; with little work, spread it over all SMs by capping the
-    // number of live slots per lane group (latency, not throughput, is what matters then)
-    const long long groups = (long long)sm_count() * (skb_slots_per_cta() / 4);
-    int slot_cap = (int)((pm.n_local + groups - 1) / groups);
-    if (slot_cap > 4) slot_cap = 4;
-    if (slot_cap < 1) slot_cap = 1;
-    const long long per_cta = (long long)(skb_slots_per_cta() / 4) * slot_cap;
-    long long ctas = (pm.n_local + per_cta - 1) / per_cta;
+    // persistent grid: one CTA per SM.  With little work (latency-, not throughput-bound) spread it
+    // over all SMs and run only as many warps per CTA as there are slot-loads of problems: fewer
+    // warps per scheduler share the FP64 tensor pipe, so every iteration returns sooner.
+    const long long spw = skb_slots_per_warp();
+    long long ctas = (pm.n_local + spw - 1) / spw;
     if (ctas > sm_count()) ctas = sm_count();
-    rc = skb_launch(props, K, cost, prm, pm, ws.setup, ws.scratch, (int)ctas, slot_cap, out, iters, absorptions,
-                    status, ws.counter_fast, ws.redo, ws.n_redo, st);
+    long long warp_cap = (pm.n_local + spw * ctas - 1) / (spw * ctas);
+    if (warp_cap > skb_warps()) warp_cap = skb_warps();
+    if (warp_cap < 1) warp_cap = 1;
+    const int slot_cap = 2;
+    rc = skb_launch(props, K, cost, prm, pm, ws.setup, ws.scratch, (int)ctas, slot_cap, (int)warp_cap, out, iters,
+                    absorptions, status, ws.counter_fast, ws.redo, ws.n_redo, st);
     if (rc) return rc;
     // problems the scaled form could not represent (normally none): reference-form kernel
     return sinkhorn_ref_launch(props, K, cost, prm, pm, ws.redo, ws.n_redo, SK_REDO_CAP, out, iters, absorptions,

@@ -22,8 +22,10 @@ size_t skb_setup_bytes(int KP);
 size_t skb_smem_bytes(int KP);
 size_t skb_scratch_bytes(int KP, int ctas);
 int skb_slots_per_cta();
+int skb_slots_per_warp();
+int skb_warps();
 int skb_launch(const double *props, int K, const double *cost, const SkParams &prm, const PairMap &pm,
-               double *setup, double *scratch, int ctas, int slot_cap, double *out, int *iters, int *absn,
+               double *setup, double *scratch, int ctas, int slot_cap, int warp_cap, double *out, int *iters, int *absn,
                int *status, unsigned long long *counter, long long *redo, unsigned long long *n_redo,
                cudaStream_t st);
 

@@ -86,7 +86,7 @@ __device__ __forceinline__ int swz(int row, int col) { return col ^ ((row & 1) <
 
 template <int KP, bool FULL>
 __global__ void __launch_bounds__(SKB_WARPS * 32, 1)
-sinkhorn_batched_kernel(const double *__restrict__ props, int K, SkParams prm, PairMap pm, int slot_cap,
+sinkhorn_batched_kernel(const double *__restrict__ props, int K, SkParams prm, PairMap pm, int slot_cap, int warp_cap,
                         const double *__restrict__ gK0, const double *__restrict__ gK0T,
                         const double *__restrict__ gMK, const double *__restrict__ gc0,
                         double *__restrict__ scratch,  // [gridDim * WARPS * 8][2][KP] rea / reb
@@ -105,6 +105,10 @@ sinkhorn_batched_kernel(const double *__restrict__ props, int K, SkParams prm, P
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     double *U = sUV + (size_t)warp * 2 * KP * PS;  // U[row][slot], then V
     double *V = U + KP * PS;
+    // small K (latency-bound batches): the marginals a, b of the warp's 8 slots live in shared memory
+    constexpr bool STAGE_AB = KP <= 32;
+    double *sA = sUV + (size_t)SKB_WARPS * 2 * KP * PS + (size_t)warp * 2 * SKB_SPW * KP;  // [slot][KP], then b
+    double *sB = sA + SKB_SPW * KP;
     for (int e = threadIdx.x; e < KP * KP; e += blockDim.x) {
         const int r = e / KP, c = e - r * KP;
         sK0[r * KP + swz(r, c)] = gK0[e];
@@ -112,6 +116,7 @@ sinkhorn_batched_kernel(const double *__restrict__ props, int K, SkParams prm, P
     }
     for (int e = threadIdx.x; e < KP; e += blockDim.x) sc0[e] = gc0[e];
     __syncthreads();
+    if (warp >= warp_cap) return;  // small batches: fewer warps per scheduler = shorter iteration latency
 
     // C-fragment ownership: lane (g, t) holds rows {8m + g} of the slots {2t, 2t + 1}
     const int g = lane >> 2, t = lane & 3;
@@ -141,9 +146,14 @@ sinkhorn_batched_kernel(const double *__restrict__ props, int K, SkParams prm, P
         s_ii[h] = 0; s_abs[h] = 0; s_hasabs[h] = false; s_pend[h] = false; s_force[h] = false; \
         s_fresh[h] = true; s_bad[h] = false;                                                \
         _Pragma("unroll") for (int m = 0; m < MT; ++m) {                                    \
-            const double v0 = (s_act[h] && ROW_OK(8 * m + g)) ? invK : 0.0;                 \
+            const bool rok = s_act[h] && ROW_OK(8 * m + g);                                 \
+            const double v0 = rok ? invK : 0.0;                                             \
             Uc[8 * m * PS + h] = v0;                                                        \
             Vc[8 * m * PS + h] = v0;                                                        \
+            if (STAGE_AB) {                                                                 \
+                sA[(2 * t + h) * KP + 8 * m + g] = rok ? __ldg(pa[h] + 8 * m) : 0.0;        \
+                sB[(2 * t + h) * KP + 8 * m + g] = rok ? __ldg(pb[h] + 8 * m) : 0.0;        \
+            }                                                                               \
         }                                                                                   \
     } while (0)
 
@@ -178,7 +188,8 @@ sinkhorn_batched_kernel(const double *__restrict__ props, int K, SkParams prm, P
         for (int h = 0; h < 2; ++h)
 #pragma unroll
             for (int m = 0; m < MT; ++m)
-                num[m][h] = (s_act[h] && ROW_OK(8 * m + g)) ? __ldg(pb[h] + 8 * m) : 0.0;
+                num[m][h] = STAGE_AB ? sB[(2 * t + h) * KP + 8 * m + g]
+                                     : ((s_act[h] && ROW_OK(8 * m + g)) ? __ldg(pb[h] + 8 * m) : 0.0);
 
         // ---- resolve the pending convergence check / iteration cap of the previous iteration ----
         bool stop[2];
@@ -295,7 +306,8 @@ sinkhorn_batched_kernel(const double *__restrict__ props, int K, SkParams prm, P
             for (int h = 0; h < 2; ++h)
 #pragma unroll
                 for (int m = 0; m < MT; ++m)
-                    num[m][h] = (s_act[h] && ROW_OK(8 * m + g)) ? __ldg(pa[h] + 8 * m) : 0.0;
+                    num[m][h] = STAGE_AB ? sA[(2 * t + h) * KP + 8 * m + g]
+                                         : ((s_act[h] && ROW_OK(8 * m + g)) ? __ldg(pa[h] + 8 * m) : 0.0);
             double un[MT][2];
             double mxu[2] = {0.0, 0.0}, smu[2] = {0.0, 0.0};
 #pragma unroll
@@ -378,7 +390,8 @@ sinkhorn_batched_kernel(const double *__restrict__ props, int K, SkParams prm, P
 size_t skb_setup_bytes(int KP) { return sizeof(double) * ((size_t)3 * KP * KP + KP); }
 size_t skb_smem_bytes(int KP)
 {
-    return sizeof(double) * ((size_t)2 * KP * KP + KP + (size_t)SKB_WARPS * 2 * KP * SKB_SPW);
+    const size_t stage = KP <= 32 ? (size_t)SKB_WARPS * 2 * SKB_SPW * KP : 0;  // a, b of every slot
+    return sizeof(double) * ((size_t)2 * KP * KP + KP + (size_t)SKB_WARPS * 2 * KP * SKB_SPW + stage);
 }
 size_t skb_scratch_bytes(int KP, int ctas)
 {
@@ -386,9 +399,11 @@ size_t skb_scratch_bytes(int KP, int ctas)
 }
 int skb_pad(int K) { return K <= 16 ? 16 : (K <= 32 ? 32 : 64); }
 int skb_slots_per_cta() { return SKB_WARPS * SKB_SPW; }
+int skb_slots_per_warp() { return SKB_SPW; }
+int skb_warps() { return SKB_WARPS; }
 
 template <int KP, bool FULL>
-static int skb_launch_t(const double *props, int K, const SkParams &prm, const PairMap &pm, int slot_cap,
+static int skb_launch_t(const double *props, int K, const SkParams &prm, const PairMap &pm, int slot_cap, int warp_cap,
                         const double *setup, double *scratch, int ctas, double *out, int *iters, int *absn,
                         int *status, unsigned long long *counter, long long *redo, unsigned long long *n_redo,
                         cudaStream_t st)
@@ -398,13 +413,13 @@ static int skb_launch_t(const double *props, int K, const SkParams &prm, const P
                                     (int)smem));
     const double *K0 = setup, *K0T = K0 + KP * KP, *MK = K0T + KP * KP, *c0 = MK + KP * KP;
     sinkhorn_batched_kernel<KP, FULL><<<ctas, SKB_WARPS * 32, smem, st>>>(
-        props, K, prm, pm, slot_cap, K0, K0T, MK, c0, scratch, out, iters, absn, status, counter, redo, n_redo);
+        props, K, prm, pm, slot_cap, warp_cap, K0, K0T, MK, c0, scratch, out, iters, absn, status, counter, redo, n_redo);
     PILOT_LAUNCH_CHECK();
     return 0;
 }
 
 int skb_launch(const double *props, int K, const double *cost, const SkParams &prm, const PairMap &pm,
-               double *setup, double *scratch, int ctas, int slot_cap, double *out, int *iters, int *absn,
+               double *setup, double *scratch, int ctas, int slot_cap, int warp_cap, double *out, int *iters, int *absn,
                int *status, unsigned long long *counter, long long *redo, unsigned long long *n_redo,
                cudaStream_t st)
 {
@@ -413,7 +428,7 @@ int skb_launch(const double *props, int K, const double *cost, const SkParams &p
                                         setup + 3 * KP * KP);
     PILOT_LAUNCH_CHECK();
 #define SKB_GO(KPV, FULLV) \
-    return skb_launch_t<KPV, FULLV>(props, K, prm, pm, slot_cap, setup, scratch, ctas, out, iters, absn, status, \
+    return skb_launch_t<KPV, FULLV>(props, K, prm, pm, slot_cap, warp_cap, setup, scratch, ctas, out, iters, absn, status, \
                                     counter, redo, n_redo, st)
     if (KP == 16) { if (K == 16) SKB_GO(16, true); SKB_GO(16, false); }
     if (KP == 32) { if (K == 32) SKB_GO(32, true); SKB_GO(32, false); }
