@@ -37,9 +37,14 @@ constexpr int SKB_SPW = 8;  // slots (problems in flight) per warp = panel colum
 // K0, K0^T, M o K0 (all KP x KP, zero padded) and c0 = K0^T (1/K) into the workspace
 __global__ void skb_setup_kernel(const double *__restrict__ M, int K, int KP, double reg,
                                  double *__restrict__ K0, double *__restrict__ K0T,
-                                 double *__restrict__ MK, double *__restrict__ c0)
+                                 double *__restrict__ MK, double *__restrict__ c0, int *__restrict__ asym)
 {
     const int n = KP * KP;
+    // asym != 0 when M differs from its transpose (asym was zeroed by the caller)
+    for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < K * K; e += gridDim.x * blockDim.x) {
+        const int i = e / K, j = e - i * K;
+        if (i < j && M[i * K + j] != M[j * K + i]) *asym = 1;
+    }
     for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < n; e += gridDim.x * blockDim.x) {
         const int i = e / KP, j = e - i * KP;
         double k0 = 0.0, mk = 0.0;
@@ -84,7 +89,7 @@ __device__ __forceinline__ double fast_div(double x, double y)
 // swizzled panel / matrix addressing: column ^ 8 on odd rows
 __device__ __forceinline__ int swz(int row, int col) { return col ^ ((row & 1) << 3); }
 
-template <int KP, bool FULL>
+template <int KP, bool FULL, bool SYM>
 __global__ void __launch_bounds__(SKB_WARPS * 32, 1)
 sinkhorn_batched_kernel(const double *__restrict__ props, int K, SkParams prm, PairMap pm, int slot_cap, int warp_cap,
                         const double *__restrict__ gK0, const double *__restrict__ gK0T,
@@ -98,9 +103,13 @@ sinkhorn_batched_kernel(const double *__restrict__ props, int K, SkParams prm, P
     constexpr int KS = KP / 4;   // k-steps of 4
     constexpr int PS = SKB_SPW;  // panel row stride (doubles): 64-byte rows, conflict-free as they are
     extern __shared__ __align__(16) unsigned char smem_raw[];
+    // symmetric cost (always so in PILOT: squareform(pdist)): K0^T == K0, and the second matrix slot
+    // holds M o K0 for the final cost instead; otherwise it holds K0^T and M o K0 is read from L2
+    constexpr bool sym = SYM;
     double *sK0 = reinterpret_cast<double *>(smem_raw);  // [i][swz(i, j)]
-    double *sK0T = sK0 + KP * KP;                        // [j][swz(j, i)]
-    double *sc0 = sK0T + KP * KP;
+    double *sSecond = sK0 + KP * KP;
+    double *sK0T = sym ? sK0 : sSecond;                  // [j][swz(j, i)]
+    double *sc0 = sSecond + KP * KP;
     double *sUV = sc0 + KP;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     double *U = sUV + (size_t)warp * 2 * KP * PS;  // U[row][slot], then V
@@ -112,7 +121,8 @@ sinkhorn_batched_kernel(const double *__restrict__ props, int K, SkParams prm, P
     for (int e = threadIdx.x; e < KP * KP; e += blockDim.x) {
         const int r = e / KP, c = e - r * KP;
         sK0[r * KP + swz(r, c)] = gK0[e];
-        sK0T[r * KP + swz(r, c)] = gK0T[e];
+        if (sym) sSecond[e] = gMK[e];                    // plain [i][j]
+        else sSecond[r * KP + swz(r, c)] = gK0T[e];
     }
     for (int e = threadIdx.x; e < KP; e += blockDim.x) sc0[e] = gc0[e];
     __syncthreads();
@@ -232,10 +242,15 @@ sinkhorn_batched_kernel(const double *__restrict__ props, int K, SkParams prm, P
                 double cost = 0.0;
                 if (stt >= 0) {
                     // cost = sum_j Vt_j * sum_i (M o K0)_ij Ut_i ; lane = column j
+                    const double *mk = sym ? sSecond : gMK;
                     for (int j = lane; j < KP; j += 32) {
-                        double wj = 0.0;
-                        for (int i = 0; i < K; ++i) wj = fma(__ldg(gMK + i * KP + j), U[i * PS + col], wj);
-                        cost = fma(V[j * PS + col], wj, cost);
+                        double w0 = 0.0, w1 = 0.0;
+                        for (int i = 0; i + 1 < K; i += 2) {
+                            w0 = fma(mk[i * KP + j], U[i * PS + col], w0);
+                            w1 = fma(mk[(i + 1) * KP + j], U[(i + 1) * PS + col], w1);
+                        }
+                        if (K & 1) w0 = fma(mk[(K - 1) * KP + j], U[(K - 1) * PS + col], w0);
+                        cost = fma(V[j * PS + col], w0 + w1, cost);
                     }
                     cost = warp_sum_d(cost);
                 }
@@ -387,7 +402,7 @@ sinkhorn_batched_kernel(const double *__restrict__ props, int K, SkParams prm, P
 #undef ROW_OK
 }
 
-size_t skb_setup_bytes(int KP) { return sizeof(double) * ((size_t)3 * KP * KP + KP); }
+size_t skb_setup_bytes(int KP) { return sizeof(double) * ((size_t)3 * KP * KP + KP + 32); }
 size_t skb_smem_bytes(int KP)
 {
     const size_t stage = KP <= 32 ? (size_t)SKB_WARPS * 2 * SKB_SPW * KP : 0;  // a, b of every slot
@@ -402,17 +417,17 @@ int skb_slots_per_cta() { return SKB_WARPS * SKB_SPW; }
 int skb_slots_per_warp() { return SKB_SPW; }
 int skb_warps() { return SKB_WARPS; }
 
-template <int KP, bool FULL>
+template <int KP, bool FULL, bool SYM>
 static int skb_launch_t(const double *props, int K, const SkParams &prm, const PairMap &pm, int slot_cap, int warp_cap,
                         const double *setup, double *scratch, int ctas, double *out, int *iters, int *absn,
                         int *status, unsigned long long *counter, long long *redo, unsigned long long *n_redo,
                         cudaStream_t st)
 {
     const size_t smem = skb_smem_bytes(KP);
-    PILOT_CUDA(cudaFuncSetAttribute(sinkhorn_batched_kernel<KP, FULL>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    PILOT_CUDA(cudaFuncSetAttribute(sinkhorn_batched_kernel<KP, FULL, SYM>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                     (int)smem));
     const double *K0 = setup, *K0T = K0 + KP * KP, *MK = K0T + KP * KP, *c0 = MK + KP * KP;
-    sinkhorn_batched_kernel<KP, FULL><<<ctas, SKB_WARPS * 32, smem, st>>>(
+    sinkhorn_batched_kernel<KP, FULL, SYM><<<ctas, SKB_WARPS * 32, smem, st>>>(
         props, K, prm, pm, slot_cap, warp_cap, K0, K0T, MK, c0, scratch, out, iters, absn, status, counter, redo, n_redo);
     PILOT_LAUNCH_CHECK();
     return 0;
@@ -424,12 +439,24 @@ int skb_launch(const double *props, int K, const double *cost, const SkParams &p
                cudaStream_t st)
 {
     const int KP = skb_pad(K);
+    PILOT_CUDA(cudaMemsetAsync(setup + 3 * KP * KP + KP, 0, sizeof(double), st));
     skb_setup_kernel<<<8, 256, 0, st>>>(cost, K, KP, prm.reg, setup, setup + KP * KP, setup + 2 * KP * KP,
-                                        setup + 3 * KP * KP);
+                                        setup + 3 * KP * KP, reinterpret_cast<int *>(setup + 3 * KP * KP + KP));
     PILOT_LAUNCH_CHECK();
-#define SKB_GO(KPV, FULLV) \
-    return skb_launch_t<KPV, FULLV>(props, K, prm, pm, slot_cap, warp_cap, setup, scratch, ctas, out, iters, absn, status, \
-                                    counter, redo, n_redo, st)
+    // symmetric cost (the PILOT case) selects the variant that keeps M o K0 in shared memory; the
+    // flag comes from the setup kernel (one 4-byte read-back, the only host sync of this call)
+    int h_asym = 1;
+    PILOT_CUDA(cudaMemcpyAsync(&h_asym, reinterpret_cast<int *>(setup + 3 * KP * KP + KP), sizeof(int),
+                               cudaMemcpyDeviceToHost, st));
+    PILOT_CUDA(cudaStreamSynchronize(st));
+#define SKB_GO(KPV, FULLV)                                                                                        \
+    do {                                                                                                          \
+        if (h_asym == 0)                                                                                          \
+            return skb_launch_t<KPV, FULLV, true>(props, K, prm, pm, slot_cap, warp_cap, setup, scratch, ctas, out, \
+                                                  iters, absn, status, counter, redo, n_redo, st);                 \
+        return skb_launch_t<KPV, FULLV, false>(props, K, prm, pm, slot_cap, warp_cap, setup, scratch, ctas, out,   \
+                                               iters, absn, status, counter, redo, n_redo, st);                    \
+    } while (0)
     if (KP == 16) { if (K == 16) SKB_GO(16, true); SKB_GO(16, false); }
     if (KP == 32) { if (K == 32) SKB_GO(32, true); SKB_GO(32, false); }
     if (K == 64) SKB_GO(64, true);

@@ -91,6 +91,20 @@ def test_sinkhorn_pairs_match_oracle(K, reg, algo):
     assert ((st == 0) | (st == 1)).all()
 
 
+@pytest.mark.parametrize("K", [12, 64])
+def test_sinkhorn_asymmetric_cost(K):
+    """wasserstein_d accepts any cost matrix: a non-symmetric one keeps K0^T in shared memory."""
+    S = 10
+    P, _ = synth.make_pairs(S, K, seed=77)
+    M = np.random.default_rng(3).random((K, K))
+    M /= M.max()
+    rng = ops.make_range(S * S, _lib.PAIRS_FULL)
+    out, iters, absn, status = ops.sinkhorn_pairs(dev(P), dev(M), 0.1, rng, want_info=True)
+    want, witers, wabs = po.sinkhorn_rows(P, M, 0.1, 0, S)
+    np.testing.assert_array_equal(iters.cpu().numpy().reshape(S, S), witers)
+    np.testing.assert_allclose(out.cpu().numpy().reshape(S, S), want, rtol=SK_RTOL)
+
+
 def test_sinkhorn_zero_mass_goes_through_reference_form():
     # zero masses make POT's log(u) = -inf -> NaN roll-back; the batched kernel must hand these over
     K, S = 10, 4
