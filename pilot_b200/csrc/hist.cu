@@ -57,15 +57,18 @@ hist_kernel(const int *__restrict__ ct, const int *__restrict__ smp, long long n
         for (int q = 0; q < 4; ++q) {
             // out-of-range codes are dropped; the host detects them as sum(counts) != n_cells
             const bool ok = valid && (unsigned)cc[q] < (unsigned)K && (unsigned)ss[q] < (unsigned)S;
-            const int key = ok ? ss[q] * K + cc[q] : -1 - lane;  // invalid lanes form singleton groups
-            const unsigned grp = __match_any_sync(0xffffffffu, key);
             if (ok) {
+                const int key = ss[q] * K + cc[q];
                 const unsigned long long idx = (unsigned long long)(v * 4 + q);
                 first_min(&s_fct[cc[q]], idx);
                 first_min(&s_fsm[ss[q]], idx);
-                if (lane == __ffs(grp) - 1) {
-                    if (SMEM_COUNTS) atomicAdd(&s_cnt[key], (unsigned)__popc(grp));
-                    else atomicAdd(&counts[key], (unsigned long long)__popc(grp));
+                if (SMEM_COUNTS) {
+                    // ATOMS.POPC.INC: the hardware merges the lanes of the warp that hit the same counter
+                    atomicAdd(&s_cnt[key], 1u);
+                } else {
+                    // L2 atomics: merge equal keys of the warp first (match.any), one atomic per group
+                    const unsigned grp = __match_any_sync(__activemask(), key);
+                    if (lane == __ffs(grp) - 1) atomicAdd(&counts[key], (unsigned long long)__popc(grp));
                 }
             }
         }

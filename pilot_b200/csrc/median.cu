@@ -226,18 +226,16 @@ static int median_run(const T *X, long long n, int D, long long ldx, const int *
 
 
 // =====================================================================================
-// sampled-pivot streaming path
+// sampled-pivot streaming path over TYPE-SORTED row tiles
 // =====================================================================================
-constexpr int MED_SCAP = 4096;          // samples kept per type
-template <typename T> struct MedChunk { static constexpr int V = sizeof(T) == 4 ? 8 : 4; };  // dims per pivot CTA
-constexpr int MED_PIV_THREADS = 256;    // 8 warps: one per dim of the chunk
-constexpr int MED_SAMPLE_BLOCK = 32;    // consecutive rows per sample block
+constexpr int MED_SCAP = 2048;          // samples per (type, dim) for the pivots
 constexpr double MED_SIGMAS = 5.5;      // half-width of the bracket in binomial sigmas
-constexpr int MED_STAGE_BYTES = 32768;   // candidates staged in shared memory by the finish kernel
-constexpr int MED_G = 32;               // candidate sub-lists per (type, dim): spreads the binning atomics
+constexpr int MS_PROC = 4;              // tile processors (64 threads) per stream CTA
+constexpr int MS_MAXCH = 4;             // column chunks of 64 per processor -> D <= 256
+constexpr int MS_STAGE_BYTES = 32768;   // candidates staged in shared memory by the finish kernel
+constexpr int MS_MAXITEMS_PER_TYPE = 2048;
 
-// shared-memory reduction without the compiler's warp-aggregation collective (which costs far
-// more than the conflict it avoids when the bins are spread)
+// shared-memory reduction without the compiler's warp-aggregation collective
 __device__ __forceinline__ void red_shared_inc(unsigned int *p)
 {
     const unsigned addr = (unsigned)__cvta_generic_to_shared(p);
@@ -248,231 +246,113 @@ template <typename T> struct Inf;
 template <> struct Inf<float> { __device__ static float pos() { return __int_as_float(0x7f800000); } };
 template <> struct Inf<double> { __device__ static double pos() { return __longlong_as_double(0x7ff0000000000000LL); } };
 
-struct MedianSampling {
-    long long m_s;      // sampled rows
-    long long nblocks;  // sample blocks
-    long long bstride;  // rows between block starts
+// workspace header (first 64 bytes, zeroed per call)
+struct MsHeader {
+    unsigned int fail;          // pairs that took the exact full-column fallback (diagnostic)
+    unsigned int item_counter;  // work queue of the stream kernel
+    unsigned int n_items;
+    unsigned int pad[13];
 };
 
-static MedianSampling median_sampling(long long n, int K)
-{
-    MedianSampling sp;
-    long long target = (long long)MED_SCAP * K;
-    if (target > n) target = n;
-    sp.nblocks = (target + MED_SAMPLE_BLOCK - 1) / MED_SAMPLE_BLOCK;
-    if (sp.nblocks < 1) sp.nblocks = 1;
-    sp.bstride = (n / sp.nblocks) / MED_SAMPLE_BLOCK * MED_SAMPLE_BLOCK;  // warp-aligned sample blocks
-    if (sp.bstride < MED_SAMPLE_BLOCK) sp.bstride = MED_SAMPLE_BLOCK;
-    while (sp.nblocks > 1 && (sp.nblocks - 1) * sp.bstride + MED_SAMPLE_BLOCK > n) --sp.nblocks;
-    sp.m_s = sp.nblocks * MED_SAMPLE_BLOCK;
-    if (sp.m_s > n) sp.m_s = n;
-    return sp;
-}
-
-template <typename T> struct MedianWs2 {
+template <typename T> struct MsWs {
+    MsHeader *hdr;
+    unsigned int *cursor;      // K: scatter reservation cursors
     unsigned long long *type_cnt;  // K
-    unsigned long long *cand_total;  // 1: running offset allocator
-    unsigned int *ccnt;            // KD: candidates appended
-    unsigned int *fail;            // 1: pairs that needed the full-column fallback (diagnostic)
-    unsigned int *cap;             // KD
-    unsigned long long *coff;      // KD
-    T *piv;                        // KD * 2
-    unsigned int *partial;         // ctasB * KD * 2
-    T *cand;                       // cand_capacity
-    unsigned long long cand_capacity;
-    unsigned int *scnt;            // K: sampled rows seen per type
-    int *slist;                    // K x MED_SCAP sampled row ids
-    unsigned int *log_cnt;         // TW: records in each warp's private candidate log
-    unsigned int *log_flag;        // 1: some log overflowed -> every pair takes the exact fallback
-    int *log_kd;                   // TW x log_cap
-    T *log_val;                    // TW x log_cap
-    unsigned int log_cap;
+    unsigned int *type_off;    // K + 1
+    int *item_first;           // K + 1
+    int *item_k;               // NI
+    unsigned int *item_r0, *item_r1;  // NI: range inside sorted_rows
+    unsigned int *sorted_rows; // n
+    T *piv;                    // KD x 2
+    unsigned int *cnt;         // NI x D x 5: below, eq_lo, eq_hi, nan, ncand
+    T *cand;                   // NI x D x capi
+    unsigned int item_rows, capi, ni_max;
 };
 
-__global__ void median_count_kernel(const int *__restrict__ code, long long n, int K, MedianSampling sp,
-                                    unsigned long long *__restrict__ type_cnt, unsigned int *__restrict__ scnt,
-                                    int *__restrict__ slist)
+__global__ void msort_count_kernel(const int *__restrict__ code, long long n, int K,
+                                   unsigned long long *__restrict__ type_cnt)
 {
     extern __shared__ unsigned int s_cnt[];
     for (int i = threadIdx.x; i < K; i += blockDim.x) s_cnt[i] = 0u;
     __syncthreads();
     const long long stride = (long long)gridDim.x * blockDim.x;
-    const long long nround = (n + stride - 1) / stride;
-    const int lane = threadIdx.x & 31;
-    for (long long it = 0; it < nround; ++it) {
-        const long long i = it * stride + (long long)blockIdx.x * blockDim.x + threadIdx.x;
-        const int k = i < n ? __ldg(code + i) : -1;
-        const bool ok = (unsigned)k < (unsigned)K;
-        const unsigned grp = __match_any_sync(0xffffffffu, ok ? k : -1 - lane);
-        if (ok && lane == __ffs(grp) - 1) atomicAdd(&s_cnt[k], (unsigned)__popc(grp));
-        // block-strided row sample: rows [b*bstride, b*bstride + 32) for b < nblocks
-        const long long b = i / sp.bstride;
-        const bool smp = ok && b < sp.nblocks && (i - b * sp.bstride) < MED_SAMPLE_BLOCK;
-        if (!__any_sync(0xffffffffu, smp)) continue;  // warp-aligned blocks: ~1 warp-step in 8 gets here
-        const unsigned sg = __match_any_sync(0xffffffffu, smp ? k : -1 - lane);
-        if (smp) {
-            const int leader = __ffs(sg) - 1;
-            unsigned base = 0;
-            if (lane == leader) base = atomicAdd(&scnt[k], (unsigned)__popc(sg));
-            base = __shfl_sync(sg, base, leader);
-            const unsigned pos = base + __popc(sg & ((1u << lane) - 1u));
-            if (pos < (unsigned)MED_SCAP) slist[(size_t)k * MED_SCAP + pos] = (int)i;
-        }
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const int k = __ldg(code + i);
+        if ((unsigned)k < (unsigned)K) atomicAdd(&s_cnt[k], 1u);  // ATOMS.POPC.INC: hardware warp aggregation
     }
     __syncthreads();
     for (int i = threadIdx.x; i < K; i += blockDim.x)
         if (s_cnt[i]) atomicAdd(&type_cnt[i], (unsigned long long)s_cnt[i]);
 }
 
-// the streaming pass: one coalesced read of X.  Warp w of the grid owns a contiguous row range;
-// lanes walk consecutive elements (lane = dimension, D >= 32, so the 32 lanes of one step never
-// share a (type, dim) counter and the shared-memory read-modify-write needs no atomics); MED_U
-// independent loads per lane are in flight before the first is consumed.  Elements inside the
-// bracket go to the warp's PRIVATE append log (ballot prefix, plain stores, no atomics).
-constexpr int MED_U = 8;
-
+// one CTA: type offsets and the work items (type, row range) of the stream kernel
 template <typename T>
-__global__ void __launch_bounds__(1024)
-median_stream_kernel(const T *__restrict__ X, long long n, int D, long long ldx, const int *__restrict__ code,
-                     int K, int W, MedianWs2<T> ws)
+__global__ void __launch_bounds__(256) msort_plan_kernel(int K, MsWs<T> ws)
 {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int KD = K * D;
-    T *spiv = reinterpret_cast<T *>(smem_raw);                                   // KD x 2 (lo, hi)
-    unsigned int *rare = reinterpret_cast<unsigned int *>(spiv + 2 * (size_t)KD);  // KD: x == hi | NaN << 16 (atomics)
-    unsigned int *cnt = rare + KD;                                               // W x KD: x < lo | x == lo << 16
-    for (int i = threadIdx.x; i < 2 * KD; i += blockDim.x) spiv[i] = ws.piv[i];
-    for (int i = threadIdx.x; i < (W + 1) * KD; i += blockDim.x) rare[i] = 0u;
-    __syncthreads();
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    {
-        unsigned int *mycnt = cnt + (size_t)warp * KD;
-        const long long TW = (long long)gridDim.x * W;
-        const long long gw = (long long)blockIdx.x * W + warp;
-        const long long r_begin = gw * n / TW, r_end = (gw + 1) * n / TW;
-        int *lkd = ws.log_kd + (size_t)gw * ws.log_cap;
-        T *lval = ws.log_val + (size_t)gw * ws.log_cap;
-        unsigned nlog = 0;
-        // all index arithmetic below is 32-bit and local to my row range (rows_per_warp * ldx < 2^31)
-        const int nrows = (int)(r_end - r_begin);
-        const int e_end = nrows * D;  // elements of my range, flat (row-major, d fastest)
-        const T *Xw = X + r_begin * ldx;
-        const int *cw = code + r_begin;
-        const int ldx32 = (int)ldx;
-        const unsigned lt_mask = (1u << lane) - 1u;
-        auto consume = [&](T x, int kd) {
-            bool cand = false;
-            if (kd >= 0) {
-                const T lo = spiv[2 * kd], hi = spiv[2 * kd + 1];
-                const unsigned inc0 = x < lo ? 1u : (x == lo ? 0x10000u : 0u);
-                if (inc0) mycnt[kd] += inc0;
-                if ((x == hi && hi != lo) || x != x) {
-                    // plain shared-memory reduction (inline PTX keeps the compiler from wrapping this
-                    // rare path in its warp-aggregation collective)
-                    const unsigned addr = (unsigned)__cvta_generic_to_shared(rare + kd);
-                    asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(addr), "r"(x != x ? 0x10000u : 1u) : "memory");
-                }
-                cand = x > lo && x < hi;
-            }
-            const unsigned bal = __ballot_sync(0xffffffffu, cand);
-            if (cand) {
-                const unsigned pos = nlog + __popc(bal & lt_mask);
-                if (pos < ws.log_cap) { lkd[pos] = kd; lval[pos] = x; }
-            }
-            nlog += __popc(bal);
-        };
-
-        // The warp walks its contiguous range in blocks of 32 * MED_U elements.  (rowb, remb) =
-        // (eb / D, eb % D) is kept incrementally; the <= 256/D + 2 type codes a block touches are
-        // loaded by the first lanes and handed out by shuffle; X is read through one running
-        // pointer with compile-time offsets (the matrix is contiguous: ldx == D).
-        constexpr int BLK = 32 * MED_U;
-        const int blk_rows = BLK / D, blk_rem = BLK - blk_rows * D;
-        int rowb = 0, remb = 0;
-        const T *p = Xw + lane;
-        int eb = 0;
-        for (; eb < e_end; eb += BLK, p += BLK) {
-            const bool full = eb + BLK <= e_end;
-            const int cval = (rowb + lane < nrows) ? __ldg(cw + rowb + lane) : -1;
-            T xv[MED_U];
-#pragma unroll
-            for (int j = 0; j < MED_U; ++j) xv[j] = (full || eb + 32 * j + lane < e_end) ? p[32 * j] : (T)0;
-            int d = remb + lane, ro = 0;
-            if (d >= D) { d -= D; ro = 1; }
-#pragma unroll
-            for (int j = 0; j < MED_U; ++j) {
-                const int k = __shfl_sync(0xffffffffu, cval, ro);
-                const bool ok = full || eb + 32 * j + lane < e_end;
-                consume(xv[j], (ok && (unsigned)k < (unsigned)K) ? k * D + d : -1);
-                d += 32;
-                if (d >= D) { d -= D; ++ro; }  // D >= 32: at most one wrap per step
-            }
-            rowb += blk_rows;
-            remb += blk_rem;
-            if (remb >= D) { remb -= D; ++rowb; }
+    if (threadIdx.x == 0) {
+        unsigned off = 0;
+        int ni = 0;
+        for (int k = 0; k < K; ++k) {
+            const unsigned nk = (unsigned)ws.type_cnt[k];
+            ws.type_off[k] = off;
+            ws.item_first[k] = ni;
+            ni += (int)((nk + ws.item_rows - 1) / ws.item_rows);
+            off += nk;
         }
-        if (lane == 0) {
-            ws.log_cnt[gw] = nlog < ws.log_cap ? nlog : ws.log_cap;
-            if (nlog > ws.log_cap) atomicOr(ws.log_flag, 1u);
-        }
+        ws.type_off[K] = off;
+        ws.item_first[K] = ni;
+        ws.hdr->n_items = (unsigned)ni;
     }
     __syncthreads();
-    // per-CTA partial table: [cta][kd][4] = x < lo, x == lo, x == hi, NaN
-    unsigned int *out = ws.partial + (size_t)blockIdx.x * KD * 4;
-    for (int i = threadIdx.x; i < KD; i += blockDim.x) {
-        unsigned a = 0, b = 0;
-        for (int w = 0; w < W; ++w) {
-            const unsigned v = cnt[(size_t)w * KD + i];
-            a += v & 0xffffu;
-            b += v >> 16;
+    for (int k = 0; k < K; ++k) {
+        const unsigned off = ws.type_off[k], nk = ws.type_off[k + 1] - off;
+        const int first = ws.item_first[k], cnt = ws.item_first[k + 1] - first;
+        for (int j = threadIdx.x; j < cnt; j += blockDim.x) {
+            const unsigned r = (unsigned)j * ws.item_rows;
+            ws.item_k[first + j] = k;
+            ws.item_r0[first + j] = off + r;
+            ws.item_r1[first + j] = off + (r + ws.item_rows < nk ? r + ws.item_rows : nk);
         }
-        const unsigned rr = rare[i];
-        *reinterpret_cast<uint4 *>(out + 4 * (size_t)i) = make_uint4(a, b, rr & 0xffffu, rr >> 16);
     }
 }
 
-// regroup the warp logs by (type, dim): one CTA per log, one returning atomic per record -- here
-// thousands of independent records are in flight, so the atomics are throughput- not latency-bound
+// counting-sort scatter of the row ids by type: CTA-local histogram, one global reservation per
+// (CTA, type), shared-memory cursors for the positions inside the reservation
 template <typename T>
 __global__ void __launch_bounds__(256)
-median_bin_kernel(MedianWs2<T> ws)
+msort_scatter_kernel(const int *__restrict__ code, long long n, int K, MsWs<T> ws)
 {
-    const size_t gw = blockIdx.x;
-    const unsigned nrec = ws.log_cnt[gw];
-    const int *lkd = ws.log_kd + gw * ws.log_cap;
-    const T *lval = ws.log_val + gw * ws.log_cap;
-    const unsigned g = (unsigned)(gw % MED_G);
-    for (unsigned i0 = threadIdx.x; i0 < nrec; i0 += 4 * blockDim.x) {
-        int kd[4];
-        T v[4];
-        unsigned capv[4], slot[4];
-        unsigned long long off[4];
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-            const unsigned i = i0 + u * blockDim.x;
-            kd[u] = i < nrec ? lkd[i] : -1;
-            v[u] = i < nrec ? lval[i] : (T)0;
+    extern __shared__ unsigned int s_u[];  // hist[K], base[K]
+    unsigned int *hist = s_u, *base = s_u + K;
+    for (int i = threadIdx.x; i < K; i += blockDim.x) hist[i] = 0u;
+    __syncthreads();
+    const long long per = (n + gridDim.x - 1) / gridDim.x;
+    const long long c0 = (long long)blockIdx.x * per, c1 = c0 + per < n ? c0 + per : n;
+    for (long long i = c0 + threadIdx.x; i < c1; i += blockDim.x) {
+        const int k = __ldg(code + i);
+        if ((unsigned)k < (unsigned)K) atomicAdd(&hist[k], 1u);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < K; i += blockDim.x) {
+        base[i] = hist[i] ? ws.type_off[i] + atomicAdd(&ws.cursor[i], hist[i]) : 0u;
+        hist[i] = 0u;
+    }
+    __syncthreads();
+    for (long long i = c0 + threadIdx.x; i < c1; i += blockDim.x) {
+        const int k = __ldg(code + i);
+        if ((unsigned)k < (unsigned)K) {
+            const unsigned pos = atomicAdd(&hist[k], 1u);
+            ws.sorted_rows[base[k] + pos] = (unsigned)i;
         }
-#pragma unroll
-        for (int u = 0; u < 4; ++u)
-            if (kd[u] >= 0) {
-                capv[u] = ws.cap[kd[u]];
-                off[u] = ws.coff[kd[u]];
-                slot[u] = atomicAdd(&ws.ccnt[(size_t)kd[u] * MED_G + g], 1u);
-            }
-#pragma unroll
-        for (int u = 0; u < 4; ++u)
-            if (kd[u] >= 0 && slot[u] < capv[u]) ws.cand[off[u] + (unsigned long long)g * capv[u] + slot[u]] = v[u];
     }
 }
 
-// CTA-level radix select of two ranks over an arbitrary key source (candidate lists or a full
-// column).  `known_prefix`/`first_shift`: digits above first_shift are already known to equal
-// known_prefix for every key of interest (all candidates lie between the two pivots).
+// CTA-level radix select of two ranks over an arbitrary key source.  `known_prefix`/`first_shift`:
+// digits above first_shift are already known to equal known_prefix for every key of interest.
 template <typename T, typename Src>
 __device__ void cta_select2_raw(Src src, long long r0, long long r1, unsigned int *hist /*[512]*/,
-                            long long *sh /*[4]*/, typename KeyOf<T>::type known_prefix, int first_shift,
-                            T &out0, T &out1)
+                                long long *sh /*[4]*/, typename KeyOf<T>::type known_prefix, int first_shift,
+                                T &out0, T &out1)
 {
     using KO = KeyOf<T>;
     using Key = typename KO::type;
@@ -508,9 +388,8 @@ __device__ void cta_select2_raw(Src src, long long r0, long long r1, unsigned in
             const unsigned long long excl = incl - mine;
             const unsigned long long rank = (unsigned long long)(warp ? q1 : q0);
             if (rank >= excl && rank < incl) {
-                unsigned long long run = excl;
+                unsigned long long run = excl, below = excl;
                 int digit = lane * 8 + 7;
-                unsigned long long below = excl;
                 bool found = false;
 #pragma unroll
                 for (int t = 0; t < 8; ++t) {
@@ -532,116 +411,224 @@ __device__ void cta_select2_raw(Src src, long long r0, long long r1, unsigned in
     out1 = KO::value(p1);
 }
 
-// one CTA per (type, dim): pivots lo/hi bracketing the median, from the type's sampled rows
+// one CTA per (type, dim): pivots lo <= hi bracketing the median, from <= MED_SCAP evenly spaced rows
+// of the type's sorted segment, gathered once into shared memory
 template <typename T>
-__global__ void __launch_bounds__(128)
-median_pivot_kernel(const T *__restrict__ X, long long n, int D, long long ldx, const int *__restrict__ code,
-                    int K, MedianSampling sp, MedianWs2<T> ws)
+__global__ void __launch_bounds__(256)
+msort_pivot_kernel(const T *__restrict__ X, int D, long long ldx, MsWs<T> ws)
 {
     using KO = KeyOf<T>;
     using Key = typename KO::type;
     constexpr int BITS = sizeof(Key) * 8;
     __shared__ unsigned int hist[512];
     __shared__ long long sh[4];
+    __shared__ T vals[MED_SCAP];
     const int kd = blockIdx.x;
     const int k = kd / D, d = kd - k * D;
-    const int ns = (int)min(ws.scnt[k], (unsigned)MED_SCAP);
-    const int *rows = ws.slist + (size_t)k * MED_SCAP;
-    const unsigned long long Nk = ws.type_cnt[k];
+    const unsigned off = ws.type_off[k];
+    const unsigned long long Nk = ws.type_off[k + 1] - off;
+    const int ns = (int)(Nk < (unsigned long long)MED_SCAP ? Nk : (unsigned long long)MED_SCAP);
     T lo = -Inf<T>::pos(), hi = Inf<T>::pos();
-    double frac = 1.0;
     if (ns >= 64) {
         const int delta = (int)ceil(0.5 * MED_SIGMAS * sqrt((double)ns)) + 1;
         const int jlo = (ns - 1) / 2 - delta, jhi = ns / 2 + delta;
         if (jlo > 0 && jhi < ns - 1) {
             const T *Xd = X + d;
-            auto smp = [&](auto f) {
-                for (int i0 = threadIdx.x; i0 < ns; i0 += 4 * 128) {
-                    T xv[4];
+            for (int i0 = threadIdx.x; i0 < ns; i0 += 4 * 256) {
+                unsigned rid[4];
 #pragma unroll
-                    for (int u = 0; u < 4; ++u) {
-                        const int i = i0 + 128 * u;
-                        xv[u] = i < ns ? Xd[(long long)__ldg(rows + i) * ldx] : (T)0;
-                    }
-#pragma unroll
-                    for (int u = 0; u < 4; ++u)
-                        if (i0 + 128 * u < ns) f(xv[u]);
+                for (int u = 0; u < 4; ++u) {
+                    const int i = i0 + 256 * u;
+                    rid[u] = i < ns ? ws.sorted_rows[off + (unsigned)(((unsigned long long)i * Nk) / (unsigned)ns)] : 0u;
                 }
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int i = i0 + 256 * u;
+                    if (i < ns) vals[i] = Xd[(long long)rid[u] * ldx];
+                }
+            }
+            __syncthreads();
+            auto smp = [&](auto f) {
+                for (int i = threadIdx.x; i < ns; i += 256) f(vals[i]);
             };
             // NaN samples carry the largest key, i.e. they sort last, as in np.sort
             cta_select2_raw<T>(smp, jlo, jhi, hist, sh, (Key)0, BITS - 8, lo, hi);
             if (hi != hi) hi = Inf<T>::pos();
             if (lo != lo) lo = -Inf<T>::pos();
-            frac = (double)(jhi - jlo + 1) / ns;
         }
     }
     if (threadIdx.x == 0) {
         ws.piv[2 * kd] = lo;
         ws.piv[2 * kd + 1] = hi;
-        // MED_G sub-lists per pair, each sized for its share (x2: the split is binomial) plus slack
-        unsigned long long want = (unsigned long long)(frac * (double)Nk * 2.0 / MED_G) + 128ULL;
-        if (want > Nk) want = Nk;
-        if (want > 0x0fffffffULL) want = 0x0fffffffULL;
-        const unsigned long long off = atomicAdd(ws.cand_total, want * MED_G);
-        unsigned int cap = (unsigned int)want;
-        if (off + want * MED_G > ws.cand_capacity) cap = 0;  // out of candidate space -> exact fallback
-        ws.cap[kd] = cap;   // per sub-list
-        ws.coff[kd] = off;  // sub-list g starts at off + g * cap
     }
 }
 
+template <int BYTES> __device__ __forceinline__ void cp_async_bytes(unsigned smem_addr, const void *src)
+{
+    if (BYTES == 16) asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_addr), "l"(src) : "memory");
+    else if (BYTES == 8) asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_addr), "l"(src) : "memory");
+    else asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_addr), "l"(src) : "memory");
+}
+
+// The streaming pass.  A tile processor (64 threads) takes work items = (type, <= item_rows rows of
+// that type); rows are gathered with cp.async into a double-buffered shared-memory tile (each row is
+// one contiguous D-element read), then THREAD = COLUMN: the pivots of (type, d) and the five
+// counters live in registers, elements strictly inside the bracket go to the thread's private list.
+// No atomics, no ballots, no tables: ~10 instructions per element.
+template <typename T, int VB>  // VB = bytes per cp.async (row starts and D * sizeof(T) are multiples of it)
+__global__ void __launch_bounds__(MS_PROC * 64)
+msort_stream_kernel(const T *__restrict__ X, int D, long long ldx, int TR, MsWs<T> ws)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ unsigned int s_item[MS_PROC];
+    const int proc = threadIdx.x >> 6, ptid = threadIdx.x & 63, pw = ptid >> 5, lane = threadIdx.x & 31;
+    T *tile = reinterpret_cast<T *>(smem_raw) + (size_t)proc * 2 * TR * D;  // [2][TR][D]
+    const unsigned tile_s = (unsigned)__cvta_generic_to_shared(tile);
+    const unsigned n_items = ws.hdr->n_items;
+    const unsigned capi = ws.capi;
+    const int row_bytes = D * (int)sizeof(T);
+    const int nvec = row_bytes / VB;  // cp.async chunks per row
+    for (;;) {
+        if (ptid == 0) s_item[proc] = atomicAdd(&ws.hdr->item_counter, 1u);
+        asm volatile("bar.sync %0, 64;" ::"r"(proc + 1) : "memory");
+        const unsigned it = s_item[proc];
+        asm volatile("bar.sync %0, 64;" ::"r"(proc + 1) : "memory");
+        if (it >= n_items) break;
+        const int k = ws.item_k[it];
+        const unsigned r0 = ws.item_r0[it], r1 = ws.item_r1[it];
+        T lo[MS_MAXCH], hi[MS_MAXCH];
+        unsigned c_below[MS_MAXCH], c_eqlo[MS_MAXCH], c_eqhi[MS_MAXCH], c_nan[MS_MAXCH], c_cand[MS_MAXCH];
+#pragma unroll
+        for (int ch = 0; ch < MS_MAXCH; ++ch) {
+            const int d = ch * 64 + ptid;
+            lo[ch] = d < D ? ws.piv[2 * ((size_t)k * D + d)] : (T)0;
+            hi[ch] = d < D ? ws.piv[2 * ((size_t)k * D + d) + 1] : (T)0;
+            c_below[ch] = c_eqlo[ch] = c_eqhi[ch] = c_nan[ch] = c_cand[ch] = 0u;
+        }
+        const int ntiles = (int)((r1 - r0 + TR - 1) / TR);
+        auto load_tile = [&](int t, int buf) {
+            const unsigned rb = r0 + (unsigned)t * TR;
+            const unsigned rid_mine = (rb + lane < r1 && lane < TR) ? ws.sorted_rows[rb + lane] : 0u;
+            const unsigned dst = tile_s + (unsigned)(buf * TR) * row_bytes;
+            const int nrow = (int)(r1 - rb < (unsigned)TR ? r1 - rb : (unsigned)TR);
+            for (int row = pw; row < nrow; row += 2) {
+                const unsigned rid = __shfl_sync(0xffffffffu, rid_mine, row);
+                const char *src = reinterpret_cast<const char *>(X + (long long)rid * ldx);
+                for (int c = lane; c < nvec; c += 32) cp_async_bytes<VB>(dst + row * row_bytes + c * VB, src + c * VB);
+            }
+            asm volatile("cp.async.commit_group;" ::: "memory");
+        };
+        load_tile(0, 0);
+        for (int t = 0; t < ntiles; ++t) {
+            const int buf = t & 1;
+            if (t + 1 < ntiles) {
+                load_tile(t + 1, buf ^ 1);
+                asm volatile("cp.async.wait_group 1;" ::: "memory");
+            } else {
+                asm volatile("cp.async.wait_group 0;" ::: "memory");
+            }
+            asm volatile("bar.sync %0, 64;" ::"r"(proc + 1) : "memory");
+            const unsigned rb = r0 + (unsigned)t * TR;
+            const int rows = (int)(r1 - rb < (unsigned)TR ? r1 - rb : (unsigned)TR);
+            const T *src = tile + (size_t)buf * TR * D;
+#pragma unroll
+            for (int ch = 0; ch < MS_MAXCH; ++ch) {
+                const int d = ch * 64 + ptid;
+                if (d < D) {
+                    T *cl = ws.cand + ((size_t)it * D + d) * capi;
+                    const T l = lo[ch], h = hi[ch];
+                    const bool hneql = h != l;
+                    unsigned nb = c_below[ch], ne = c_eqlo[ch], nh = c_eqhi[ch], nn = c_nan[ch], nc = c_cand[ch];
+                    const T *col = src + d;
+#pragma unroll 4
+                    for (int row = 0; row < rows; ++row) {
+                        const T x = col[row * D];
+                        nb += x < l ? 1u : 0u;
+                        ne += x == l ? 1u : 0u;
+                        nh += (x == h && hneql) ? 1u : 0u;
+                        nn += x != x ? 1u : 0u;
+                        if (x > l && x < h) {
+                            if (nc < capi) cl[nc] = x;
+                            ++nc;
+                        }
+                    }
+                    c_below[ch] = nb; c_eqlo[ch] = ne; c_eqhi[ch] = nh; c_nan[ch] = nn; c_cand[ch] = nc;
+                }
+            }
+            asm volatile("bar.sync %0, 64;" ::"r"(proc + 1) : "memory");  // tile buffer free again
+        }
+#pragma unroll
+        for (int ch = 0; ch < MS_MAXCH; ++ch) {
+            const int d = ch * 64 + ptid;
+            if (d < D) {
+                unsigned int *o = ws.cnt + ((size_t)it * D + d) * 5;
+                o[0] = c_below[ch]; o[1] = c_eqlo[ch]; o[2] = c_eqhi[ch]; o[3] = c_nan[ch]; o[4] = c_cand[ch];
+            }
+        }
+    }
+}
+
+// one CTA per (type, dim): rank bookkeeping over the type's items, selection inside the candidates,
+// exact fallback over the type's own rows when the bracket missed or a list overflowed
 template <typename T>
 __global__ void __launch_bounds__(128)
-median_finish_kernel(const T *__restrict__ X, long long n, int D, long long ldx, const int *__restrict__ code,
-                     int K, int ctasB, MedianWs2<T> ws, T *__restrict__ cent, double *__restrict__ cent64)
+msort_finish_kernel(const T *__restrict__ X, int D, long long ldx, MsWs<T> ws, T *__restrict__ cent,
+                    double *__restrict__ cent64)
 {
     using KO = KeyOf<T>;
     using Key = typename KO::type;
     constexpr int BITS = sizeof(Key) * 8;
+    constexpr int STAGE = MS_STAGE_BYTES / (int)sizeof(T);
     __shared__ unsigned int hist[512];
     __shared__ long long sh[4];
-    __shared__ unsigned long long s_sum[4];
-    __shared__ unsigned int s_goff[MED_G + 1];
-    constexpr int MED_STAGE = MED_STAGE_BYTES / (int)sizeof(T);
-    __shared__ T s_stage[MED_STAGE];
+    __shared__ unsigned long long s_sum[5];
+    __shared__ unsigned int s_off[MS_MAXITEMS_PER_TYPE + 1];
+    __shared__ T s_stage[STAGE];
+    __shared__ int s_over;
     const int kd = blockIdx.x;
     const int k = kd / D, d = kd - k * D;
-    if (threadIdx.x < 4) s_sum[threadIdx.x] = 0ULL;
+    const int i0 = ws.item_first[k], i1 = ws.item_first[k + 1];
+    const int nit = i1 - i0;
+    if (threadIdx.x < 5) s_sum[threadIdx.x] = 0ULL;
+    if (threadIdx.x == 0) s_over = nit > MS_MAXITEMS_PER_TYPE ? 1 : 0;
     __syncthreads();
     {
-        unsigned long long a0 = 0, a1 = 0, a2 = 0, a3 = 0;
-        for (int c = threadIdx.x; c < ctasB; c += blockDim.x) {
-            const uint4 v = *reinterpret_cast<const uint4 *>(ws.partial + ((size_t)c * K * D + kd) * 4);
-            a0 += v.x; a1 += v.y; a2 += v.z; a3 += v.w;
+        unsigned long long a[4] = {0, 0, 0, 0};
+        for (int q = threadIdx.x; q < nit; q += blockDim.x) {
+            const unsigned int *c = ws.cnt + ((size_t)(i0 + q) * D + d) * 5;
+            a[0] += c[0]; a[1] += c[1]; a[2] += c[2]; a[3] += c[3];
+            const unsigned nc = c[4];
+            if (nc > ws.capi) s_over = 1;
+            if (q < MS_MAXITEMS_PER_TYPE) s_off[q + 1] = nc < ws.capi ? nc : ws.capi;
         }
-        atomicAdd(&s_sum[0], a0); atomicAdd(&s_sum[1], a1); atomicAdd(&s_sum[2], a2); atomicAdd(&s_sum[3], a3);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) atomicAdd(&s_sum[j], a[j]);
     }
-    const unsigned int capv = ws.cap[kd];
-    // sub-list sizes: one lane per sub-list, warp scan for the offsets
-    __shared__ int s_over;
-    if (threadIdx.x == 0) s_over = *ws.log_flag != 0u ? 1 : 0;
     __syncthreads();
     if (threadIdx.x < 32) {
-        static_assert(MED_G == 32, "one lane per sub-list");
-        const unsigned c = ws.ccnt[(size_t)kd * MED_G + threadIdx.x];
-        const unsigned cc = c < capv ? c : capv;
-        if (c > capv) s_over = 1;
-        unsigned incl = cc;
+        // inclusive scan of s_off[1..m] by one warp, 32 entries per step
+        const int m = nit < MS_MAXITEMS_PER_TYPE ? nit : MS_MAXITEMS_PER_TYPE;
+        unsigned carry = 0;
+        for (int base = 0; base < m; base += 32) {
+            const int q = base + threadIdx.x;
+            unsigned v = q < m ? s_off[q + 1] : 0u;
 #pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const unsigned v = __shfl_up_sync(0xffffffffu, incl, o);
-            if (threadIdx.x >= o) incl += v;
+            for (int o = 1; o < 32; o <<= 1) {
+                const unsigned u = __shfl_up_sync(0xffffffffu, v, o);
+                if ((int)threadIdx.x >= o) v += u;
+            }
+            if (q < m) s_off[q + 1] = v + carry;
+            carry += __shfl_sync(0xffffffffu, v, 31);
         }
-        s_goff[threadIdx.x] = incl - cc;
-        if (threadIdx.x == 31) s_goff[32] = incl;
+        if (threadIdx.x == 0) { s_off[0] = 0; s_sum[4] = carry; }
     }
     __syncthreads();
     const bool overflow = s_over != 0;
     const long long below = (long long)s_sum[0], eq_lo = (long long)s_sum[1], eq_hi = (long long)s_sum[2];
-    const long long n_nan = (long long)s_sum[3];
-    const long long Nk = (long long)ws.type_cnt[k];
+    const long long n_nan = (long long)s_sum[3], nmid = (long long)s_sum[4];
+    const unsigned toff = ws.type_off[k];
+    const long long Nk = (long long)ws.type_off[k + 1] - toff;
     const long long nvalid = Nk - n_nan;
-    const long long nmid = s_goff[MED_G];
     T med;
     if (nvalid <= 0) {
         med = (T)NAN;
@@ -659,33 +646,30 @@ median_finish_kernel(const T *__restrict__ X, long long n, int D, long long ldx,
             if (r < eq_hi) return 3;
             return 4;
         };
-        long long i0 = 0, i1 = 0;
-        const int g0 = region(r0, i0), g1 = region(r1, i1);
+        long long j0 = 0, j1 = 0;
+        const int g0 = region(r0, j0), g1 = region(r1, j1);
         T v0, v1;
         if (overflow || g0 == 0 || g0 == 4 || g1 == 0 || g1 == 4) {
-            // exact fallback: radix select over the whole column of this type
-            if (threadIdx.x == 0) atomicAdd(ws.fail, 1u);
+            // exact fallback: radix select over this type's own rows
+            if (threadIdx.x == 0) atomicAdd(&ws.hdr->fail, 1u);
             auto col = [&](auto f) {
-                for (long long i = threadIdx.x; i < n; i += blockDim.x)
-                    if (__ldg(code + i) == k) {
-                        const T x = X[i * ldx + d];
-                        if (x == x) f(x);
-                    }
+                for (long long i = threadIdx.x; i < Nk; i += blockDim.x) {
+                    const T x = X[(long long)ws.sorted_rows[toff + i] * ldx + d];
+                    if (x == x) f(x);
+                }
             };
             cta_select2_raw<T>(col, r0, r1, hist, sh, (Key)0, BITS - 8, v0, v1);
         } else {
             T m0 = lo, m1 = lo;
             if (g0 == 2 || g1 == 2) {
-                const T *cl = ws.cand + ws.coff[kd];
-                // gather the MED_G sub-lists into shared memory once (all loads in flight together);
-                // longer lists are read from global memory on every pass
-                const bool staged = nmid <= MED_STAGE;
+                const bool staged = nmid <= STAGE;
                 if (staged) {
-                    for (int idx = threadIdx.x; idx < MED_G * 32; idx += blockDim.x) {
-                        const int g = idx >> 5, l5 = idx & 31;
-                        const unsigned cg = s_goff[g + 1] - s_goff[g];
-                        const T *seg = cl + (unsigned long long)g * capv;
-                        for (unsigned i = l5; i < cg; i += 32) s_stage[s_goff[g] + i] = seg[i];
+                    // warp w copies the lists of items w, w + 4, ... (each a short contiguous run)
+                    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+                    for (int q = warp; q < nit; q += 4) {
+                        const T *cl = ws.cand + ((size_t)(i0 + q) * D + d) * ws.capi;
+                        const unsigned o = s_off[q], c = s_off[q + 1] - o;
+                        for (unsigned i = lane; i < c; i += 32) s_stage[o + i] = cl[i];
                     }
                     __syncthreads();
                 }
@@ -693,10 +677,10 @@ median_finish_kernel(const T *__restrict__ X, long long n, int D, long long ldx,
                     if (staged) {
                         for (unsigned i = threadIdx.x; i < (unsigned)nmid; i += blockDim.x) f(s_stage[i]);
                     } else {
-                        for (int g = 0; g < MED_G; ++g) {
-                            const unsigned cg = s_goff[g + 1] - s_goff[g];
-                            const T *seg = cl + (unsigned long long)g * capv;
-                            for (unsigned i = threadIdx.x; i < cg; i += blockDim.x) f(seg[i]);
+                        for (int q = 0; q < nit; ++q) {
+                            const T *cl = ws.cand + ((size_t)(i0 + q) * D + d) * ws.capi;
+                            const unsigned c = s_off[q + 1] - s_off[q];
+                            for (unsigned i = threadIdx.x; i < c; i += blockDim.x) f(cl[i]);
                         }
                     }
                 };
@@ -709,7 +693,7 @@ median_finish_kernel(const T *__restrict__ X, long long n, int D, long long ldx,
                     while (first > 0 && (kl >> first) == (kh >> first)) first -= 8;
                     if (first < BITS - 8) prefix = (Key)((kl >> (first + 8)) << (first + 8));
                 }
-                cta_select2_raw<T>(lst, g0 == 2 ? i0 : 0, g1 == 2 ? i1 : 0, hist, sh, prefix, first, m0, m1);
+                cta_select2_raw<T>(lst, g0 == 2 ? j0 : 0, g1 == 2 ? j1 : 0, hist, sh, prefix, first, m0, m1);
             }
             v0 = g0 == 1 ? lo : (g0 == 3 ? hi : m0);
             v1 = g1 == 1 ? lo : (g1 == 3 ? hi : m1);
@@ -724,122 +708,123 @@ median_finish_kernel(const T *__restrict__ X, long long n, int D, long long ldx,
     }
 }
 
-static int median_stream_warps(int K, int D, size_t elt)
-{
-    const size_t kd = (size_t)K * D;
-    const size_t fixed = kd * 2 * elt + kd * sizeof(unsigned int), tab = kd * sizeof(unsigned int);
-    const size_t budget = 208 * 1024;
-    if (fixed + tab > budget) return 0;
-    size_t w = (budget - fixed) / tab;
-    return (int)(w > 32 ? 32 : w);
-}
-
 static size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
 
-static unsigned int median_log_cap(long long n, int D, long long TW)
+struct MsPlan {
+    unsigned item_rows, capi, ni_max;
+    int TR;
+};
+
+static MsPlan ms_plan(long long n, int K, int D, size_t elt)
 {
-    // expected ~10 % of a warp's elements are candidates; allow 3.5x that plus slack
-    const double per_warp = (double)n * D / (double)TW;
-    double c = 0.35 * per_warp + 2048.0;
-    if (c > 4.0e9) c = 4.0e9;
-    return (unsigned int)c;
+    MsPlan p;
+    long long ir = (n + (long long)sm_count() * 16 - 1) / ((long long)sm_count() * 16);
+    ir = (ir + 31) / 32 * 32;
+    if (ir < 128) ir = 128;
+    p.item_rows = (unsigned)ir;
+    p.capi = (unsigned)(0.35 * (double)ir) + 32;
+    p.ni_max = (unsigned)(n / ir) + (unsigned)K + 2;
+    long long tr = (48 * 1024) / ((long long)MS_PROC * 2 * D * (long long)elt);  // ~48 KB of tiles per CTA
+    if (tr > 32) tr = 32;
+    p.TR = (int)(tr < 4 ? 4 : tr);
+    return p;
 }
 
 template <typename T>
-static size_t median_ws2_bytes(long long n, int K, int D, int ctasB, int W)
+static size_t ms_ws_bytes(long long n, int K, int D)
 {
+    const MsPlan p = ms_plan(n, K, D, sizeof(T));
     const size_t kd = (size_t)K * D;
-    const long long TW = (long long)ctasB * W;
-    const size_t lc = median_log_cap(n, D, TW);
-    size_t b = 0;
-    b += align256((size_t)K * 8 + 8);              // type_cnt + cand_total
-    b += align256(kd * MED_G * 4 + 4);             // ccnt (MED_G sub-lists) + fail
-    b += align256((size_t)K * 4 + 4);              // scnt + log_flag
-    b += align256((size_t)TW * 4);                 // log_cnt
-    b += align256(kd * 4);                         // cap
-    b += align256(kd * 8);                         // coff
-    b += align256(kd * 2 * sizeof(T));             // piv
-    b += align256((size_t)K * MED_SCAP * 4);       // slist
-    b += align256((size_t)ctasB * kd * 4 * 4);     // partial: 4 counters per pair and CTA
-    b += align256((size_t)TW * lc * 4);            // log_kd
-    b += align256((size_t)TW * lc * sizeof(T));    // log_val
-    b += align256(((size_t)(0.3 * (double)n * D) + kd * 256 * MED_G) * sizeof(T));  // candidates
+    size_t b = 256;                                   // header
+    b += align256((size_t)K * 4);                     // cursor
+    b += align256((size_t)K * 8);                     // type_cnt
+    b += align256((size_t)(K + 1) * 4) * 2;           // type_off, item_first
+    b += align256((size_t)p.ni_max * 4) * 3;          // item_k, item_r0, item_r1
+    b += align256((size_t)n * 4);                     // sorted_rows
+    b += align256(kd * 2 * sizeof(T));                // piv
+    b += align256((size_t)p.ni_max * D * 5 * 4);      // cnt
+    b += align256((size_t)p.ni_max * D * p.capi * sizeof(T));  // cand
     return b;
 }
 
 template <typename T>
-static int median_run_sampled(const T *X, long long n, int D, long long ldx, const int *code, int K, T *cent,
-                              double *cent64, void *workspace, int W, cudaStream_t st)
+static int median_run_sorted(const T *X, long long n, int D, long long ldx, const int *code, int K, T *cent,
+                             double *cent64, void *workspace, cudaStream_t st)
 {
+    const MsPlan pl = ms_plan(n, K, D, sizeof(T));
     const size_t kd = (size_t)K * D;
-    const int ctasB = sm_count();
-    const long long TW = (long long)ctasB * W;
-    MedianWs2<T> ws;
+    MsWs<T> ws;
     unsigned char *p = (unsigned char *)workspace;
-    ws.type_cnt = (unsigned long long *)p; ws.cand_total = ws.type_cnt + K; p += align256((size_t)K * 8 + 8);
-    ws.ccnt = (unsigned int *)p; ws.fail = ws.ccnt + kd * MED_G; p += align256(kd * MED_G * 4 + 4);
-    ws.scnt = (unsigned int *)p; ws.log_flag = ws.scnt + K; p += align256((size_t)K * 4 + 4);
-    ws.log_cnt = (unsigned int *)p; p += align256((size_t)TW * 4);
+    ws.hdr = (MsHeader *)p; p += 256;
+    ws.cursor = (unsigned int *)p; p += align256((size_t)K * 4);
+    ws.type_cnt = (unsigned long long *)p; p += align256((size_t)K * 8);
     const size_t zero_bytes = (size_t)(p - (unsigned char *)workspace);
-    ws.cap = (unsigned int *)p; p += align256(kd * 4);
-    ws.coff = (unsigned long long *)p; p += align256(kd * 8);
+    ws.type_off = (unsigned int *)p; p += align256((size_t)(K + 1) * 4);
+    ws.item_first = (int *)p; p += align256((size_t)(K + 1) * 4);
+    ws.item_k = (int *)p; p += align256((size_t)pl.ni_max * 4);
+    ws.item_r0 = (unsigned int *)p; p += align256((size_t)pl.ni_max * 4);
+    ws.item_r1 = (unsigned int *)p; p += align256((size_t)pl.ni_max * 4);
+    ws.sorted_rows = (unsigned int *)p; p += align256((size_t)n * 4);
     ws.piv = (T *)p; p += align256(kd * 2 * sizeof(T));
-    ws.slist = (int *)p; p += align256((size_t)K * MED_SCAP * 4);
-    ws.partial = (unsigned int *)p; p += align256((size_t)ctasB * kd * 4 * 4);
-    ws.log_cap = median_log_cap(n, D, TW);
-    ws.log_kd = (int *)p; p += align256((size_t)TW * ws.log_cap * 4);
-    ws.log_val = (T *)p; p += align256((size_t)TW * ws.log_cap * sizeof(T));
+    ws.cnt = (unsigned int *)p; p += align256((size_t)pl.ni_max * D * 5 * 4);
     ws.cand = (T *)p;
-    ws.cand_capacity = (unsigned long long)(0.3 * (double)n * D) + kd * 256 * MED_G;
+    ws.item_rows = pl.item_rows; ws.capi = pl.capi; ws.ni_max = pl.ni_max;
     PILOT_CUDA(cudaMemsetAsync(workspace, 0, zero_bytes, st));
-    const MedianSampling sp = median_sampling(n, K);
-    {
-        long long blocks = (n + 1023) / 1024;
-        const long long cap = (long long)sm_count() * 8;
-        if (blocks > cap) blocks = cap;
-        median_count_kernel<<<(unsigned)blocks, 256, K * sizeof(unsigned int), st>>>(code, n, K, sp, ws.type_cnt,
-                                                                                    ws.scnt, ws.slist);
-        PILOT_LAUNCH_CHECK();
-    }
-    median_pivot_kernel<T><<<(unsigned)kd, 128, 0, st>>>(X, n, D, ldx, code, K, sp, ws);
+    long long blocks = (n + 2047) / 2048;
+    const long long cap = (long long)sm_count() * 8;
+    if (blocks > cap) blocks = cap;
+    if (blocks < 1) blocks = 1;
+    msort_count_kernel<<<(unsigned)blocks, 256, K * sizeof(unsigned int), st>>>(code, n, K, ws.type_cnt);
+    PILOT_LAUNCH_CHECK();
+    msort_plan_kernel<T><<<1, 256, 0, st>>>(K, ws);
+    PILOT_LAUNCH_CHECK();
+    msort_scatter_kernel<T><<<(unsigned)blocks, 256, 2 * K * sizeof(unsigned int), st>>>(code, n, K, ws);
+    PILOT_LAUNCH_CHECK();
+    msort_pivot_kernel<T><<<(unsigned)kd, 256, 0, st>>>(X, D, ldx, ws);
     PILOT_LAUNCH_CHECK();
     {
-        const size_t smem = kd * 2 * sizeof(T) + (size_t)(W + 1) * kd * sizeof(unsigned int);
-        PILOT_CUDA(cudaFuncSetAttribute(median_stream_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        median_stream_kernel<T><<<ctasB, 32 * W, smem, st>>>(X, n, D, ldx, code, K, W, ws);
+        const size_t smem = (size_t)MS_PROC * 2 * pl.TR * D * sizeof(T);
+        // widest cp.async every row start and row length allow (the tile rows inherit the alignment)
+        const size_t rowb = (size_t)D * sizeof(T), strideb = (size_t)ldx * sizeof(T);
+        int vb = (int)sizeof(T);
+        if (rowb % 16 == 0 && strideb % 16 == 0 && ((uintptr_t)X % 16) == 0) vb = 16;
+        else if (rowb % 8 == 0 && strideb % 8 == 0 && ((uintptr_t)X % 8) == 0) vb = 8;
+#define MS_LAUNCH(VBV)                                                                                          \
+        do {                                                                                                    \
+            PILOT_CUDA(cudaFuncSetAttribute(msort_stream_kernel<T, VBV>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                            (int)smem));                                                        \
+            int per_sm = 1;                                                                                     \
+            PILOT_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, msort_stream_kernel<T, VBV>,      \
+                                                                     MS_PROC * 64, smem));                      \
+            if (per_sm < 1) per_sm = 1;                                                                         \
+            if (per_sm > 4) per_sm = 4;                                                                         \
+            msort_stream_kernel<T, VBV><<<sm_count() * per_sm, MS_PROC * 64, smem, st>>>(X, D, ldx, pl.TR, ws);  \
+        } while (0)
+        if (vb == 16) MS_LAUNCH(16);
+        else if (vb == 8) MS_LAUNCH(8);
+        else MS_LAUNCH((int)sizeof(T));
+#undef MS_LAUNCH
         PILOT_LAUNCH_CHECK();
     }
-    median_bin_kernel<T><<<(unsigned)TW, 256, 0, st>>>(ws);
-    PILOT_LAUNCH_CHECK();
-    median_finish_kernel<T><<<(unsigned)kd, 128, 0, st>>>(X, n, D, ldx, code, K, ctasB, ws, cent, cent64);
+    msort_finish_kernel<T><<<(unsigned)kd, 128, 0, st>>>(X, D, ldx, ws, cent, cent64);
     PILOT_LAUNCH_CHECK();
     return 0;
 }
 
-static bool median_use_sampled(long long n, int K, int D, size_t elt, int *W)
+static bool median_use_sorted(long long n, int K, int D)
 {
-    *W = median_stream_warps(K, D, elt);
-    // per-warp 16-bit counters: a warp must see fewer than 65536 rows
-    const long long rows_per_warp = n / ((long long)sm_count() * (*W > 0 ? *W : 1)) + 1;
-    return n >= 65536 && *W >= 2 && rows_per_warp < 60000 && D >= 32 && D <= 256;
+    return n >= 65536 && n < (1LL << 32) && D <= 64 * MS_MAXCH && K <= 4096;
 }
 
 size_t median_ws_bytes(long long n, int K, int D)
 {
     size_t a = median_ws_bytes_impl(K, D);
-    size_t b = 0;
-    for (int elt = 4; elt <= 8; elt += 4) {
-        const int W = median_stream_warps(K, D, elt);
-        if (W >= 2) {
-            const size_t c = elt == 4 ? median_ws2_bytes<float>(n, K, D, sm_count(), W)
-                                      : median_ws2_bytes<double>(n, K, D, sm_count(), W);
-            if (c > b) b = c;
-        }
+    if (median_use_sorted(n, K, D)) {
+        const size_t b = ms_ws_bytes<double>(n, K, D);
+        if (b > a) a = b;
     }
-    return a > b ? a : b;
+    return a;
 }
-
-
 }  // namespace pilot
 
 extern "C" int pilot_centroid_median(const void *X, int dtype, int64_t n_cells, int D, int64_t ldx,
@@ -856,13 +841,12 @@ extern "C" int pilot_centroid_median(const void *X, int dtype, int64_t n_cells, 
                     "pilot_centroid_median: workspace %zu < %zu bytes", workspace_bytes,
                     median_ws_bytes(n_cells, K, D));
     cudaStream_t st = (cudaStream_t)stream;
-    int W = 0;
-    if (ldx == D && median_use_sampled(n_cells, K, D, dtype == PILOT_F32 ? 4 : 8, &W)) {
+    if (median_use_sorted(n_cells, K, D)) {
         if (dtype == PILOT_F32)
-            return median_run_sampled<float>((const float *)X, n_cells, D, ldx, ct_code, K, (float *)centroids,
-                                             centroids_f64, workspace, W, st);
-        return median_run_sampled<double>((const double *)X, n_cells, D, ldx, ct_code, K, (double *)centroids,
-                                          centroids_f64, workspace, W, st);
+            return median_run_sorted<float>((const float *)X, n_cells, D, ldx, ct_code, K, (float *)centroids,
+                                            centroids_f64, workspace, st);
+        return median_run_sorted<double>((const double *)X, n_cells, D, ldx, ct_code, K, (double *)centroids,
+                                         centroids_f64, workspace, st);
     }
     if (dtype == PILOT_F32)
         return median_run<float>((const float *)X, n_cells, D, ldx, ct_code, K, (float *)centroids,

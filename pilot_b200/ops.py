@@ -118,8 +118,7 @@ def median_fallbacks(K: int, D: int, device=None) -> int:
     the exact full-column fallback of the streaming path (reads the workspace; synchronises)."""
     device = device or torch.device("cuda", torch.cuda.current_device())
     ws = _workspace(1, device)
-    off = ((K * 8 + 8 + 255) // 256) * 256 + K * D * 32 * 4  # after type_cnt/cand_total and the 32 (MED_G) sub-list counters
-    return int(ws[off:off + 4].view(torch.int32).item())
+    return int(ws[0:4].view(torch.int32).item())  # MsHeader.fail is the first word of the workspace
 
 
 def cdist(cent64: torch.Tensor, metric: str = "cosine") -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:

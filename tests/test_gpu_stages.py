@@ -85,12 +85,10 @@ def test_centroid_median_streaming_path(dtype, case):
         code = np.minimum((rng.exponential(1.2, size=n)).astype(np.int32), K - 1)  # one dominant, some rare
         code[:K] = np.arange(K)
     elif case == "adversarial_sample":
-        # sampled rows (blocks of 32 rows every n/1280 rows) all hold 0; the rest is shifted by +5
-        nblocks = -(-min(n, 4096 * K) // 32)
-        bstride = (n // nblocks) // 32 * 32
-        sampled = (np.arange(n) % bstride) < 32
-        X += 5
-        X[sampled] = 0
+        # every column sorted along the rows: the work items (contiguous row blocks of a type) around
+        # the median then lie ENTIRELY inside the pivot bracket, their candidate lists overflow and the
+        # pairs must take the exact fallback
+        X = np.sort(X, axis=0)
     cent, cent64 = ops.centroid_median(dev(X), dev(code), K)
     fallbacks = ops.median_fallbacks(K, D)
     if case == "adversarial_sample":
