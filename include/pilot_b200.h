@@ -134,7 +134,8 @@ int pilot_cdist(const double *centroids_f64, int K, int D, int metric,
  * iters / absorptions / status may be NULL.
  * algo: 0 = batched shared-Gibbs-kernel solver (fast path; problems it cannot
  *           represent are re-solved by the reference-form kernel),
- *       1 = reference-form kernel only (per-problem Gibbs kernel, literal schedule).
+ *       1 = reference-form kernel only (per-problem Gibbs kernel, literal schedule),
+ *       2 = warp-specialised variant of 0 (same results; kept for A/B measurements).
  */
 int pilot_sinkhorn_pairs(const double *props, int S, int K, const double *cost,
                          double reg, int num_iter_max, double stop_thr,

@@ -1,4 +1,4 @@
-// Shared declarations of the two Sinkhorn kernels (sinkhorn_ref.cu, sinkhorn_batched.cu).
+// Shared declarations of the Sinkhorn kernels (sinkhorn_ref.cu, sinkhorn_batched.cu, sinkhorn_ws.cu).
 #pragma once
 #include "common.cuh"
 
@@ -24,9 +24,18 @@ size_t skb_scratch_bytes(int KP, int ctas);
 int skb_slots_per_cta();
 int skb_slots_per_warp();
 int skb_warps();
-int skb_launch(const double *props, int K, const double *cost, const SkParams &prm, const PairMap &pm,
-               double *setup, double *scratch, int ctas, int slot_cap, int warp_cap, double *out, int *iters, int *absn,
-               int *status, unsigned long long *counter, long long *redo, unsigned long long *n_redo,
-               cudaStream_t st);
+int skb_setup(const double *cost, int K, const SkParams &prm, double *setup, bool *symmetric, cudaStream_t st);
+int skb_launch(const double *props, int K, const SkParams &prm, const PairMap &pm, double *setup, double *scratch,
+               int ctas, int slot_cap, int warp_cap, bool symmetric, double *out, int *iters, int *absn, int *status,
+               unsigned long long *counter, long long *redo, unsigned long long *n_redo, cudaStream_t st);
+
+// warp-specialised variant (sinkhorn_ws.cu)
+size_t skw_smem_bytes(int KP);
+size_t skw_scratch_bytes(int KP, int ctas);
+int skw_slots_per_set();
+int skw_sets();
+int skw_launch(const double *props, int K, const SkParams &prm, const PairMap &pm, double *setup, double *scratch,
+               int ctas, int slot_cap, int set_cap, bool symmetric, double *out, int *iters, int *absn, int *status,
+               unsigned long long *counter, long long *redo, unsigned long long *n_redo, cudaStream_t st);
 
 }  // namespace pilot

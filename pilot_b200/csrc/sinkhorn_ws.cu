@@ -1,71 +1,26 @@
-// Kernel (3), batched variant: all-pairs stabilised Sinkhorn with ONE shared Gibbs kernel
-// K0 = exp(-M/reg) resident in shared memory for every problem of the CTA.
-// Replaces the loop over ot.sinkhorn2(a_i, a_j, cost, reg, method="sinkhorn_stabilized")
-// (reference pilotpy/tools/Trajectory.py:513-515; schedule: SURVEY.md Appendix A.2).
+// Kernel (3), warp-specialised variant of the batched shared-Gibbs-kernel Sinkhorn solver
+// (see sinkhorn_batched.cu for the formulation; reference call site pilotpy/tools/Trajectory.py:513-515).
 //
-// Formulation.  POT keeps K = diag(e^{alpha/reg}) K0 diag(e^{beta/reg}) per problem and
-// iterates v = b/(K^T u), u = a/(K v).  With ut = e^{alpha/reg} o u and vt = e^{beta/reg} o v
-// the same iteration is vt = b/(K0^T ut), ut = a/(K0 vt) on the SHARED K0; alpha/beta only
-// matter for (i) the absorption trigger max|u|,|v| > tau, u = ut * rea with rea = e^{-alpha/reg}
-// (= 1/ut at the last absorption), and (ii) the reset u = v = 1/K at an absorption, which
-// in scaled variables is ut /= K, vt /= K.  The marginal error every `check_every` iterations
-// is || vt o (K0^T ut) - b ||, i.e. the product the next iteration needs anyway, and the
-// result is sum_ij M_ij K0_ij ut_i vt_j.  Rounding differs from the reference form at the
-// 1e-16 level with identical iteration/absorption schedules.
-//
-// Mapping.  The two matvecs of 8 problems ("slots") at a time are the dense FP64 GEMMs
-// K0^T [ut_1 .. ut_8] and K0 [vt_1 .. vt_8]; each warp runs them on the FP64 tensor path
-// (mma.sync m8n8k4, DMMA): KP/8 accumulator tiles per warp, A fragments from the shared
-// K0 / K0^T (XOR-swizzled: 2 wavefronts per fragment load, the minimum for 256 B), B fragments
-// from the warp's private 8-column U / V panel (64-byte rows: conflict free as they are).  In
-// the C-fragment layout lane (g = lane/4, t = lane%4) owns rows {8m+g} of the adjacent slots
-// {2t, 2t+1}, so the element-wise update (one 128-bit store per row), the max/err reductions
-// (3 xor-shuffles over the 8 lanes sharing t) and all per-slot state stay inside the warp: the
-// 16 warps of a CTA are independent persistent workers, no CTA barrier in the loop, a finished
-// slot is refilled at once from a global counter.  DMMA has the same peak as DFMA on B200
-// (measured 37 TFLOP/s both) but needs 1/8 of the issue slots; with 4 warps per scheduler the
-// epilogue (FP64 pipe, LSU) of three warps overlaps the DMMA stream of the fourth.
-// Problems the scaled form cannot represent (NaN/Inf, |log ut| near the FP64 range) are queued
-// for the reference-form kernel (sinkhorn_ref.cu).
+// The single-role kernel leaves the FP64 tensor pipe idle ~43 % of the time: its four warps per
+// scheduler alternate between a DMMA phase and a long latency-bound element-wise phase, and all four
+// are regularly in the element-wise phase at once.  Here the roles are split like in a Blackwell
+// GEMM: 4 MMA warps (one per scheduler) do nothing but stream matvecs -- B fragments from a slot
+// set's panel, A fragments from the shared K0 / K0^T, accumulators written to the set's result
+// buffer -- while 12 epilogue warps each own one slot set (8 problems) and do the division, the
+// reductions, absorption, convergence check, final cost and refill.  A set ping-pongs between its
+// MMA warp and its epilogue warp through a shared-memory state word (U_READY -> T_READY -> V_READY
+// -> S_READY -> U_READY ...); every MMA warp serves three sets, so the tensor pipe always has a
+// matvec to run while the other sets are in their epilogues.
 #include "sinkhorn.cuh"
 
 namespace pilot {
 
-constexpr int SKB_WARPS = 16;
-constexpr int SKB_SPW = 8;  // slots (problems in flight) per warp = panel columns
+constexpr int SKW_MMA_WARPS = 4;
+constexpr int SKW_SETS = 12;                       // one epilogue warp per set
+constexpr int SKW_WARPS = SKW_MMA_WARPS + SKW_SETS;
+constexpr int SKW_SPW = 8;                         // slots per set
 
-// K0, K0^T, M o K0 (all KP x KP, zero padded) and c0 = K0^T (1/K) into the workspace
-__global__ void skb_setup_kernel(const double *__restrict__ M, int K, int KP, double reg,
-                                 double *__restrict__ K0, double *__restrict__ K0T,
-                                 double *__restrict__ MK, double *__restrict__ c0, int *__restrict__ asym)
-{
-    const int n = KP * KP;
-    // asym != 0 when M differs from its transpose (asym was zeroed by the caller)
-    for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < K * K; e += gridDim.x * blockDim.x) {
-        const int i = e / K, j = e - i * K;
-        if (i < j && M[i * K + j] != M[j * K + i]) *asym = 1;
-    }
-    for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < n; e += gridDim.x * blockDim.x) {
-        const int i = e / KP, j = e - i * KP;
-        double k0 = 0.0, mk = 0.0;
-        if (i < K && j < K) {
-            const double m = M[i * K + j];
-            k0 = exp(-m / reg);
-            mk = m * k0;
-        }
-        K0[i * KP + j] = k0;
-        K0T[j * KP + i] = k0;
-        MK[i * KP + j] = mk;
-    }
-    if (blockIdx.x == 0)
-        for (int j = threadIdx.x; j < KP; j += blockDim.x) {
-            double s = 0.0;
-            const double u0 = 1.0 / K;
-            if (j < K)
-                for (int i = 0; i < K; ++i) s += exp(-M[i * K + j] / reg) * u0;
-            c0[j] = s;
-        }
-}
+enum { SKW_U_READY = 1, SKW_T_READY = 2, SKW_V_READY = 3, SKW_S_READY = 4, SKW_DONE = 5 };
 
 __device__ __forceinline__ void dmma884(double &c0, double &c1, double a, double b)
 {
@@ -95,50 +50,115 @@ __device__ __forceinline__ long long abs_bits(double x) { return __double_as_lon
 // wavefronts per load, the minimum (an 8-column swizzle on odd rows gave 4).
 __device__ __forceinline__ int swz(int row, int col) { return col ^ ((row & 3) << 2); }
 
+__device__ __forceinline__ int skw_load_flag(const volatile int *f) { return *f; }
+
 template <int KP, bool FULL, bool SYM>
-__global__ void __launch_bounds__(SKB_WARPS * 32, 1)
-sinkhorn_batched_kernel(const double *__restrict__ props, int K, SkParams prm, PairMap pm, int slot_cap, int warp_cap,
-                        const double *__restrict__ gK0, const double *__restrict__ gK0T,
-                        const double *__restrict__ gMK, const double *__restrict__ gc0,
-                        double *__restrict__ scratch,  // [gridDim * WARPS * 8][2][KP] rea / reb
-                        double *__restrict__ out, int *__restrict__ iters_out, int *__restrict__ abs_out,
-                        int *__restrict__ status_out, unsigned long long *__restrict__ counter,
-                        long long *__restrict__ redo_list, unsigned long long *__restrict__ n_redo)
+__global__ void __launch_bounds__(SKW_WARPS * 32, 1)
+sinkhorn_ws_kernel(const double *__restrict__ props, int K, SkParams prm, PairMap pm, int slot_cap, int set_cap,
+                   const double *__restrict__ gK0, const double *__restrict__ gK0T,
+                   const double *__restrict__ gMK, const double *__restrict__ gc0,
+                   double *__restrict__ scratch,  // [gridDim * SETS * 8][2][KP] rea / reb
+                   double *__restrict__ out, int *__restrict__ iters_out, int *__restrict__ abs_out,
+                   int *__restrict__ status_out, unsigned long long *__restrict__ counter,
+                   long long *__restrict__ redo_list, unsigned long long *__restrict__ n_redo)
 {
     constexpr int MT = KP / 8;   // accumulator row tiles
     constexpr int KS = KP / 4;   // k-steps of 4
-    constexpr int PS = SKB_SPW;  // panel row stride (doubles): 64-byte rows, conflict-free as they are
+    constexpr int PS = SKW_SPW;  // panel row stride (doubles)
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    // symmetric cost (always so in PILOT: squareform(pdist)): K0^T == K0, and the second matrix slot
-    // holds M o K0 for the final cost instead; otherwise it holds K0^T and M o K0 is read from L2
     constexpr bool sym = SYM;
     double *sK0 = reinterpret_cast<double *>(smem_raw);  // [i][swz(i, j)]
-    double *sSecond = sK0 + KP * KP;
-    double *sK0T = sym ? sK0 : sSecond;                  // [j][swz(j, i)]
+    double *sSecond = sK0 + KP * KP;                     // K0^T (swizzled), or M o K0 (plain) when symmetric
+    double *sK0T = sym ? sK0 : sSecond;
     double *sc0 = sSecond + KP * KP;
-    double *sUV = sc0 + KP;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    double *U = sUV + (size_t)warp * 2 * KP * PS;  // U[row][slot], then V
-    double *V = U + KP * PS;
-    // small K (latency-bound batches): the marginals a, b of the warp's 8 slots live in shared memory
+    double *sPan = sc0 + KP;                             // [set][U, V][KP][8]
+    double *sRes = sPan + (size_t)SKW_SETS * 2 * KP * PS;  // [set][KP][8]
     constexpr bool STAGE_AB = KP <= 32;
-    double *sA = sUV + (size_t)SKB_WARPS * 2 * KP * PS + (size_t)warp * 2 * SKB_SPW * KP;  // [slot][KP], then b
-    double *sB = sA + SKB_SPW * KP;
+    double *sAB = sRes + (size_t)SKW_SETS * KP * PS;     // [set][a, b][8][KP]  (small K only)
+    volatile int *flags = reinterpret_cast<volatile int *>(sAB + (STAGE_AB ? (size_t)SKW_SETS * 2 * SKW_SPW * KP : 0));
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     for (int e = threadIdx.x; e < KP * KP; e += blockDim.x) {
         const int r = e / KP, c = e - r * KP;
         sK0[r * KP + swz(r, c)] = gK0[e];
-        if (sym) sSecond[e] = gMK[e];                    // plain [i][j]
+        if (sym) sSecond[e] = gMK[e];
         else sSecond[r * KP + swz(r, c)] = gK0T[e];
     }
     for (int e = threadIdx.x; e < KP; e += blockDim.x) sc0[e] = gc0[e];
+    if (threadIdx.x < SKW_SETS) flags[threadIdx.x] = 0;
     __syncthreads();
-    if (warp >= warp_cap) return;  // small batches: fewer warps per scheduler = shorter iteration latency
 
-    // C-fragment ownership: lane (g, t) holds rows {8m + g} of the slots {2t, 2t + 1}
     const int g = lane >> 2, t = lane & 3;
+    const int tsw = (t & 2) << 2, gsw = g ^ ((t & 1) << 2);  // K0 fragment rows 4*ks + t: swizzle 4 * t
+
+    if (warp < SKW_MMA_WARPS) {
+        // ============================ MMA warp ============================
+        for (;;) {
+            int n_done = 0;
+            bool worked = false;
+#pragma unroll 1
+            for (int q = 0; q < SKW_SETS / SKW_MMA_WARPS; ++q) {
+                const int s = warp + SKW_MMA_WARPS * q;
+                const int stt = skw_load_flag(flags + s);
+                if (stt == SKW_DONE) { ++n_done; continue; }
+                if (stt != SKW_U_READY && stt != SKW_V_READY) continue;
+                __threadfence_block();
+                const bool phaseA = stt == SKW_U_READY;
+                const double *B = sPan + ((size_t)s * 2 + (phaseA ? 0 : 1)) * KP * PS;
+                const double *A = phaseA ? sK0 : sK0T;
+                double acc[MT][2];
+#pragma unroll
+                for (int m = 0; m < MT; ++m) { acc[m][0] = 0.0; acc[m][1] = 0.0; }
+                // software-pipelined: the fragments of k-step ks + 1 are in flight while the 8 DMMAs
+                // of step ks run (this warp is alone on its scheduler's tensor pipe, nobody else
+                // hides its shared-memory latency)
+                const double *Bp = B + t * PS + g;
+                const double *Ap = A + t * KP + gsw;
+                double an[MT], bn = Bp[0];
+#pragma unroll
+                for (int m = 0; m < MT; ++m) an[m] = Ap[(8 * m) ^ tsw];
+#pragma unroll
+                for (int ks = 0; ks < KS; ++ks) {
+                    double ac[MT];
+                    const double bc = bn;
+#pragma unroll
+                    for (int m = 0; m < MT; ++m) ac[m] = an[m];
+                    if (ks + 1 < KS) {
+                        bn = Bp[4 * (ks + 1) * PS];
+#pragma unroll
+                        for (int m = 0; m < MT; ++m) an[m] = Ap[4 * (ks + 1) * KP + ((8 * m) ^ tsw)];
+                    }
+#pragma unroll
+                    for (int m = 0; m < MT; ++m) dmma884(acc[m][0], acc[m][1], ac[m], bc);
+                }
+                double *R = sRes + (size_t)s * KP * PS + g * PS + 2 * t;
+#pragma unroll
+                for (int m = 0; m < MT; ++m)
+                    *reinterpret_cast<double2 *>(R + 8 * m * PS) = make_double2(acc[m][0], acc[m][1]);
+                __threadfence_block();
+                __syncwarp();
+                if (lane == 0) flags[s] = phaseA ? SKW_T_READY : SKW_S_READY;
+                worked = true;
+            }
+            if (n_done == SKW_SETS / SKW_MMA_WARPS) break;
+            if (!worked) __nanosleep(40);
+        }
+        return;
+    }
+
+    // ============================ epilogue warp: owns slot set `set` ============================
+    const int set = warp - SKW_MMA_WARPS;
+    volatile int *myflag = flags + set;
+    if (set >= set_cap) {
+        if (lane == 0) *myflag = SKW_DONE;
+        return;
+    }
+    double *U = sPan + (size_t)set * 2 * KP * PS;  // U[row][slot], then V
+    double *V = U + KP * PS;
+    const double *Rm = sRes + (size_t)set * KP * PS + g * PS + 2 * t;
+    double *sA = sAB + (size_t)set * 2 * SKW_SPW * KP;  // [slot][KP], then b
+    double *sB = sA + SKW_SPW * KP;
     const unsigned gmask = 0x11111111u << t;  // the 8 lanes that share my 2 slots
-    const int tsw = (t & 2) << 2, gsw = g ^ ((t & 1) << 2);             // K0 fragment rows 4*ks + t: swizzle 4 * t
-    double *wscr = scratch + ((size_t)(blockIdx.x * SKB_WARPS + warp) * SKB_SPW) * 2 * KP;
+    double *wscr = scratch + ((size_t)(blockIdx.x * SKW_SETS + set) * SKW_SPW) * 2 * KP;
     double *rea0 = wscr + (size_t)(2 * t) * 2 * KP;  // slot 2t: rea, then reb; slot 2t+1 follows
     const double invK = 1.0 / K;
     double *Uc = U + g * PS + 2 * t;  // my first element of U; rows advance by 8 * PS
@@ -151,7 +171,7 @@ sinkhorn_batched_kernel(const double *__restrict__ props, int K, SkParams prm, P
     bool s_act[2], s_hasabs[2], s_pend[2], s_force[2], s_fresh[2], s_bad[2];
 
 #define ROW_OK(r) (FULL || (r) < K)
-#define SKB_ASSIGN(h, w)                                                                    \
+#define SKW_ASSIGN(h, w)                                                                    \
     do {                                                                                    \
         sl[h] = (long long)(w);                                                             \
         s_act[h] = (w) != ~0ULL && (long long)(w) < pm.n_local;                             \
@@ -172,6 +192,17 @@ sinkhorn_batched_kernel(const double *__restrict__ props, int K, SkParams prm, P
             }                                                                               \
         }                                                                                   \
     } while (0)
+#define SKW_POST(val)                                                                       \
+    do {                                                                                    \
+        __threadfence_block();                                                              \
+        __syncwarp();                                                                       \
+        if (lane == 0) *myflag = (val);                                                     \
+    } while (0)
+#define SKW_WAIT(val)                                                                       \
+    do {                                                                                    \
+        while (skw_load_flag(myflag) != (val)) __nanosleep(64);                             \
+        __threadfence_block();                                                              \
+    } while (0)
 
     // initial fill
 #pragma unroll
@@ -179,25 +210,23 @@ sinkhorn_batched_kernel(const double *__restrict__ props, int K, SkParams prm, P
         unsigned long long w = ~0ULL;
         if (g == 0 && h < slot_cap) w = atomicAdd(counter, 1ULL);
         w = __shfl_sync(gmask, w, t);
-        SKB_ASSIGN(h, w);
+        SKW_ASSIGN(h, w);
     }
-    __syncwarp();
+    if (!__any_sync(0xffffffffu, s_act[0] || s_act[1])) {
+        if (lane == 0) *myflag = SKW_DONE;
+        return;
+    }
+    SKW_POST(SKW_U_READY);
 
     for (;;) {
-        if (!__any_sync(0xffffffffu, s_act[0] || s_act[1])) break;
-
         double acc[MT][2];
         double num[MT][2];
-        // ======================= phase A: T = K0^T Ut =======================
+        // ======================= after phase A: T = K0^T Ut is in the result buffer =======================
+        SKW_WAIT(SKW_T_READY);
 #pragma unroll
-        for (int m = 0; m < MT; ++m) { acc[m][0] = 0.0; acc[m][1] = 0.0; }
-#pragma unroll 2
-        for (int ks = 0; ks < KS; ++ks) {
-            const int kr = 4 * ks + t;
-            const double b0 = U[kr * PS + g];
-            const double *arow = sK0 + kr * KP + gsw;
-#pragma unroll
-            for (int m = 0; m < MT; ++m) dmma884(acc[m][0], acc[m][1], arow[(8 * m) ^ tsw], b0);
+        for (int m = 0; m < MT; ++m) {
+            const double2 r2 = *reinterpret_cast<const double2 *>(Rm + 8 * m * PS);
+            acc[m][0] = r2.x; acc[m][1] = r2.y;
         }
         // numerators of the v-update: b of my two slots
 #pragma unroll
@@ -278,7 +307,7 @@ sinkhorn_batched_kernel(const double *__restrict__ props, int K, SkParams prm, P
                     }
                 }
                 if (mine) {
-                    SKB_ASSIGN(h, w);
+                    SKW_ASSIGN(h, w);
 #pragma unroll
                     for (int m = 0; m < MT; ++m)
                         num[m][h] = (s_act[h] && ROW_OK(8 * m + g)) ? __ldg(pb[h] + 8 * m) : 0.0;
@@ -286,6 +315,10 @@ sinkhorn_batched_kernel(const double *__restrict__ props, int K, SkParams prm, P
             }
         }
         __syncwarp();
+        if (!__any_sync(0xffffffffu, s_act[0] || s_act[1])) {
+            SKW_POST(SKW_DONE);
+            break;
+        }
 
         // ---- v-update: Vt = b / T (my two slots are adjacent: one 128-bit store per row) ----
         long long mxv[2] = {0, 0};
@@ -307,20 +340,9 @@ sinkhorn_batched_kernel(const double *__restrict__ props, int K, SkParams prm, P
                 *reinterpret_cast<double2 *>(Vc + 8 * m * PS) = make_double2(vv[0], vv[1]);
             }
         }
-        __syncwarp();
+        SKW_POST(SKW_V_READY);
 
-        // ======================= phase B: S = K0 Vt =======================
-#pragma unroll
-        for (int m = 0; m < MT; ++m) { acc[m][0] = 0.0; acc[m][1] = 0.0; }
-#pragma unroll 2
-        for (int ks = 0; ks < KS; ++ks) {
-            const int kr = 4 * ks + t;
-            const double b0 = V[kr * PS + g];
-            const double *arow = sK0T + kr * KP + gsw;
-#pragma unroll
-            for (int m = 0; m < MT; ++m) dmma884(acc[m][0], acc[m][1], arow[(8 * m) ^ tsw], b0);
-        }
-        // ---- u-update: Ut = a / S, then the per-slot service (absorption, counters) ----
+        // numerators of the u-update while the MMA warp runs phase B
         if (s_act[0] || s_act[1]) {
 #pragma unroll
             for (int h = 0; h < 2; ++h)
@@ -328,6 +350,16 @@ sinkhorn_batched_kernel(const double *__restrict__ props, int K, SkParams prm, P
                 for (int m = 0; m < MT; ++m)
                     num[m][h] = STAGE_AB ? sA[(2 * t + h) * KP + 8 * m + g]
                                          : ((s_act[h] && ROW_OK(8 * m + g)) ? __ldg(pa[h] + 8 * m) : 0.0);
+        }
+        // ======================= after phase B: S = K0 Vt is in the result buffer =======================
+        SKW_WAIT(SKW_S_READY);
+#pragma unroll
+        for (int m = 0; m < MT; ++m) {
+            const double2 r2 = *reinterpret_cast<const double2 *>(Rm + 8 * m * PS);
+            acc[m][0] = r2.x; acc[m][1] = r2.y;
+        }
+        // ---- u-update: Ut = a / S, then the per-slot service (absorption, counters) ----
+        if (s_act[0] || s_act[1]) {
             double un[MT][2];
             long long mxu[2] = {0, 0};
 #pragma unroll
@@ -396,81 +428,58 @@ sinkhorn_batched_kernel(const double *__restrict__ props, int K, SkParams prm, P
             for (int m = 0; m < MT; ++m)
                 *reinterpret_cast<double2 *>(Uc + 8 * m * PS) = make_double2(un[m][0], un[m][1]);
         }
-        __syncwarp();
+        SKW_POST(SKW_U_READY);
     }
-#undef SKB_ASSIGN
+#undef SKW_ASSIGN
+#undef SKW_POST
+#undef SKW_WAIT
 #undef ROW_OK
 }
 
-size_t skb_setup_bytes(int KP) { return sizeof(double) * ((size_t)3 * KP * KP + KP + 32); }
-size_t skb_smem_bytes(int KP)
+size_t skw_smem_bytes(int KP)
 {
-    const size_t stage = KP <= 32 ? (size_t)SKB_WARPS * 2 * SKB_SPW * KP : 0;  // a, b of every slot
-    return sizeof(double) * ((size_t)2 * KP * KP + KP + (size_t)SKB_WARPS * 2 * KP * SKB_SPW + stage);
+    const size_t stage = KP <= 32 ? (size_t)SKW_SETS * 2 * SKW_SPW * KP : 0;
+    return sizeof(double) * ((size_t)2 * KP * KP + KP + (size_t)SKW_SETS * 3 * KP * SKW_SPW + stage) + 64;
 }
-size_t skb_scratch_bytes(int KP, int ctas)
-{
-    return sizeof(double) * (size_t)ctas * SKB_WARPS * SKB_SPW * 2 * KP;
-}
-int skb_pad(int K) { return K <= 16 ? 16 : (K <= 32 ? 32 : 64); }
-int skb_slots_per_cta() { return SKB_WARPS * SKB_SPW; }
-int skb_slots_per_warp() { return SKB_SPW; }
-int skb_warps() { return SKB_WARPS; }
+size_t skw_scratch_bytes(int KP, int ctas) { return sizeof(double) * (size_t)ctas * SKW_SETS * SKW_SPW * 2 * KP; }
+int skw_slots_per_set() { return SKW_SPW; }
+int skw_sets() { return SKW_SETS; }
 
 template <int KP, bool FULL, bool SYM>
-static int skb_launch_t(const double *props, int K, const SkParams &prm, const PairMap &pm, int slot_cap, int warp_cap,
+static int skw_launch_t(const double *props, int K, const SkParams &prm, const PairMap &pm, int slot_cap, int set_cap,
                         const double *setup, double *scratch, int ctas, double *out, int *iters, int *absn,
                         int *status, unsigned long long *counter, long long *redo, unsigned long long *n_redo,
                         cudaStream_t st)
 {
-    const size_t smem = skb_smem_bytes(KP);
-    PILOT_CUDA(cudaFuncSetAttribute(sinkhorn_batched_kernel<KP, FULL, SYM>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    const size_t smem = skw_smem_bytes(KP);
+    PILOT_CUDA(cudaFuncSetAttribute(sinkhorn_ws_kernel<KP, FULL, SYM>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                     (int)smem));
     const double *K0 = setup, *K0T = K0 + KP * KP, *MK = K0T + KP * KP, *c0 = MK + KP * KP;
-    sinkhorn_batched_kernel<KP, FULL, SYM><<<ctas, SKB_WARPS * 32, smem, st>>>(
-        props, K, prm, pm, slot_cap, warp_cap, K0, K0T, MK, c0, scratch, out, iters, absn, status, counter, redo, n_redo);
+    sinkhorn_ws_kernel<KP, FULL, SYM><<<ctas, SKW_WARPS * 32, smem, st>>>(
+        props, K, prm, pm, slot_cap, set_cap, K0, K0T, MK, c0, scratch, out, iters, absn, status, counter, redo, n_redo);
     PILOT_LAUNCH_CHECK();
     return 0;
 }
 
-// computes K0, K0^T, M o K0, c0 and reports whether the cost is symmetric (the PILOT case), which
-// selects the variant that keeps M o K0 in shared memory; the flag comes back through one 4-byte
-// read-back, the only host sync of a Sinkhorn call
-int skb_setup(const double *cost, int K, const SkParams &prm, double *setup, bool *symmetric, cudaStream_t st)
-{
-    const int KP = skb_pad(K);
-    PILOT_CUDA(cudaMemsetAsync(setup + 3 * KP * KP + KP, 0, sizeof(double), st));
-    skb_setup_kernel<<<8, 256, 0, st>>>(cost, K, KP, prm.reg, setup, setup + KP * KP, setup + 2 * KP * KP,
-                                        setup + 3 * KP * KP, reinterpret_cast<int *>(setup + 3 * KP * KP + KP));
-    PILOT_LAUNCH_CHECK();
-    int h_asym = 1;
-    PILOT_CUDA(cudaMemcpyAsync(&h_asym, reinterpret_cast<int *>(setup + 3 * KP * KP + KP), sizeof(int),
-                               cudaMemcpyDeviceToHost, st));
-    PILOT_CUDA(cudaStreamSynchronize(st));
-    *symmetric = h_asym == 0;
-    return 0;
-}
-
-// `setup` must already hold the output of skb_setup
-int skb_launch(const double *props, int K, const SkParams &prm, const PairMap &pm, double *setup, double *scratch,
-               int ctas, int slot_cap, int warp_cap, bool symmetric, double *out, int *iters, int *absn, int *status,
+// `setup` must already hold K0, K0^T, M o K0, c0 and the asymmetry flag (skb_setup_kernel)
+int skw_launch(const double *props, int K, const SkParams &prm, const PairMap &pm, double *setup, double *scratch,
+               int ctas, int slot_cap, int set_cap, bool symmetric, double *out, int *iters, int *absn, int *status,
                unsigned long long *counter, long long *redo, unsigned long long *n_redo, cudaStream_t st)
 {
     const int KP = skb_pad(K);
-    const int h_asym = symmetric ? 0 : 1;
-#define SKB_GO(KPV, FULLV)                                                                                        \
+#define SKW_GO(KPV, FULLV)                                                                                        \
     do {                                                                                                          \
-        if (h_asym == 0)                                                                                          \
-            return skb_launch_t<KPV, FULLV, true>(props, K, prm, pm, slot_cap, warp_cap, setup, scratch, ctas, out, \
+        if (symmetric)                                                                                            \
+            return skw_launch_t<KPV, FULLV, true>(props, K, prm, pm, slot_cap, set_cap, setup, scratch, ctas, out, \
                                                   iters, absn, status, counter, redo, n_redo, st);                 \
-        return skb_launch_t<KPV, FULLV, false>(props, K, prm, pm, slot_cap, warp_cap, setup, scratch, ctas, out,   \
+        return skw_launch_t<KPV, FULLV, false>(props, K, prm, pm, slot_cap, set_cap, setup, scratch, ctas, out,    \
                                                iters, absn, status, counter, redo, n_redo, st);                    \
     } while (0)
-    if (KP == 16) { if (K == 16) SKB_GO(16, true); SKB_GO(16, false); }
-    if (KP == 32) { if (K == 32) SKB_GO(32, true); SKB_GO(32, false); }
-    if (K == 64) SKB_GO(64, true);
-    SKB_GO(64, false);
-#undef SKB_GO
+    if (KP == 16) { if (K == 16) SKW_GO(16, true); SKW_GO(16, false); }
+    if (KP == 32) { if (K == 32) SKW_GO(32, true); SKW_GO(32, false); }
+    if (K == 64) SKW_GO(64, true);
+    SKW_GO(64, false);
+#undef SKW_GO
 }
 
 }  // namespace pilot

@@ -76,7 +76,7 @@ def test_emd_nonmetric_cost_and_counts():
 
 
 @pytest.mark.parametrize("K,reg", [(10, 0.1), (30, 0.1), (64, 0.1), (64, 0.01), (40, 0.02), (5, 0.5)])
-@pytest.mark.parametrize("algo", [0, 1])
+@pytest.mark.parametrize("algo", [0, 1, 2])
 def test_sinkhorn_pairs_match_oracle(K, reg, algo):
     S = 12 if reg < 0.05 else 20
     P, M = synth.make_pairs(S, K, seed=400 + K)
