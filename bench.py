@@ -244,10 +244,10 @@ class DeviceStep:
 
 
 # kernel launches of ONE DeviceStep.run() (my kernels only; memsets and torch's index_select excluded):
-# hist_init + hist (2), prior + finalize (2), median count + pivot + stream + finish (4), cdist prep/pair/norm (3),
-# sinkhorn setup + batched + reference-form redo (3) or emd (1), unpack (1)
+# hist_init + hist (2), prior + finalize (2), median count + plan + scatter + pivot + stream + finish (6),
+# cdist prep/pair/norm (3), sinkhorn setup + solver + reference-form redo (3) or emd (1), unpack (1)
 def launches_per_step(reg):
-    return 2 + 2 + 4 + 3 + (3 if reg is not None else 1) + 1
+    return 2 + 2 + 6 + 3 + (3 if reg is not None else 1) + 1
 
 
 def pair_kernel_slices(peak_fp64):
@@ -381,7 +381,8 @@ def run_b200(args):
                     "algorithmic_bytes": alg_bytes[dominant], "ms": stage_ms[dominant]}
     else:
         # the all-pairs stage dominates: algorithmic flops = sum over this rank's problems of iters * 4 K^2
-        # (SURVEY 8d); its matvecs run on the FP64 tensor path (mma.sync m8n8k4 f64)
+        # (SURVEY 8d); with K <= 32 the matvecs are DFMA chains of sinkhorn_warp_kernel (one warp per problem),
+        # above that DMMA panels of sinkhorn_batched_kernel -- same FP64 pipe, same peak
         from pilot_b200 import _lib, pairs as _pairs
         if reg is not None:
             total = s * s
@@ -394,7 +395,8 @@ def run_b200(args):
         else:
             flops, mean_iters, max_iters = float("nan"), None, None
         ach = flops / (stage_ms[dominant] * 1e-3) / 1e12
-        roofline = {"kernel": "sinkhorn_batched_kernel (all-pairs stage incl. setup/unpack)", "bound": "tensor",
+        kern = "sinkhorn_warp_kernel" if k <= 32 else "sinkhorn_batched_kernel"
+        roofline = {"kernel": kern + " (all-pairs stage incl. setup/unpack)", "bound": "tensor",
                     "achieved": ach, "peak": peaks["fp64_dmma_tflops"], "unit": "TFLOP/s",
                     "frac": ach / peaks["fp64_dmma_tflops"], "traffic": None,
                     "peak_source": "FP64 mma.sync peak measured in this run by pilot_pipe_peak (MEASURED_PEAKS.json "

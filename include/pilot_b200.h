@@ -132,10 +132,13 @@ int pilot_cdist(const double *centroids_f64, int K, int D, int metric,
  * Trajectory.py:513-515 (POT defaults: num_iter_max=1000, stop_thr=1e-9,
  * tau=1e3, check_every=20).  out[l] = sum(M * Gamma) of local problem l.
  * iters / absorptions / status may be NULL.
- * algo: 0 = batched shared-Gibbs-kernel solver (fast path; problems it cannot
- *           represent are re-solved by the reference-form kernel),
+ * algo: 0 = shared-Gibbs-kernel solvers (fast path: one warp per problem with K0
+ *           in registers for K <= 32 and a symmetric cost, else 8-problem DMMA
+ *           panels; problems they cannot represent are re-solved by the
+ *           reference-form kernel),
  *       1 = reference-form kernel only (per-problem Gibbs kernel, literal schedule),
- *       2 = warp-specialised variant of 0 (same results; kept for A/B measurements).
+ *       2 = warp-specialised variant of the DMMA-panel solver (kept for A/B measurements),
+ *       3 = DMMA-panel solver for every K <= 64.
  */
 int pilot_sinkhorn_pairs(const double *props, int S, int K, const double *cost,
                          double reg, int num_iter_max, double stop_thr,

@@ -31,7 +31,7 @@ extern "C" int pilot_sinkhorn_pairs(const double *props, int S, int K, const dou
     PILOT_CHECK_ARG(S >= 1 && K >= 1, "pilot_sinkhorn_pairs: S=%d K=%d", S, K);
     PILOT_CHECK_ARG(reg > 0.0, "pilot_sinkhorn_pairs: reg must be > 0");
     PILOT_CHECK_ARG(num_iter_max >= 1 && check_every >= 1, "pilot_sinkhorn_pairs: bad iteration parameters");
-    PILOT_CHECK_ARG(algo >= 0 && algo <= 2, "pilot_sinkhorn_pairs: algo %d", algo);
+    PILOT_CHECK_ARG(algo >= 0 && algo <= 3, "pilot_sinkhorn_pairs: algo %d", algo);
     PILOT_CHECK_ARG(sinkhorn_ref_smem(K) <= 200 * 1024, "pilot_sinkhorn_pairs: K=%d too large (max ~150)", K);
     PILOT_CHECK_ARG(workspace_bytes >= sk_ws_bytes(K), "pilot_sinkhorn_pairs: workspace %zu < %zu bytes",
                     workspace_bytes, sk_ws_bytes(K));
@@ -61,7 +61,14 @@ extern "C" int pilot_sinkhorn_pairs(const double *props, int S, int K, const dou
     // over all SMs and run only as many warps / slot sets per CTA as there are slot-loads of
     // problems: fewer of them share the FP64 tensor pipe, so every iteration returns sooner.
     const int slot_cap = 2;
-    if (algo != 2) {
+    // few cell types: one warp per problem with K0 in registers (lowest latency per iteration, and
+    // for 17..32 types also the higher throughput).  With <= 16 types half of its lanes idle, so a
+    // large batch goes to the DMMA panels instead (measured: 400 K problems, K = 12: 5.6 vs 6.9 ms).
+    const bool warp_form = algo == 0 && symmetric && K <= swk_max_k() && (K > 16 || pm.n_local < 200000);
+    if (warp_form) {
+        rc = swk_launch(props, K, prm, pm, ws.setup, out, iters, absorptions, status, ws.counter_fast, ws.redo,
+                        ws.n_redo, st);
+    } else if (algo != 2) {
         const long long spw = skb_slots_per_warp();
         long long ctas = (pm.n_local + spw - 1) / spw;
         if (ctas > sm_count()) ctas = sm_count();

@@ -1,4 +1,4 @@
-// Shared declarations of the Sinkhorn kernels (sinkhorn_ref.cu, sinkhorn_batched.cu, sinkhorn_ws.cu).
+// Shared declarations of the Sinkhorn kernels (sinkhorn_ref.cu, sinkhorn_batched.cu, sinkhorn_ws.cu, sinkhorn_warp.cu).
 #pragma once
 #include "common.cuh"
 
@@ -37,5 +37,11 @@ int skw_sets();
 int skw_launch(const double *props, int K, const SkParams &prm, const PairMap &pm, double *setup, double *scratch,
                int ctas, int slot_cap, int set_cap, bool symmetric, double *out, int *iters, int *absn, int *status,
                unsigned long long *counter, long long *redo, unsigned long long *n_redo, cudaStream_t st);
+
+// one warp per problem, K0 in registers (sinkhorn_warp.cu): K <= swk_max_k(), symmetric cost
+int swk_max_k();
+int swk_launch(const double *props, int K, const SkParams &prm, const PairMap &pm, const double *setup, double *out,
+               int *iters, int *absn, int *status, unsigned long long *counter, long long *redo,
+               unsigned long long *n_redo, cudaStream_t st);
 
 }  // namespace pilot
