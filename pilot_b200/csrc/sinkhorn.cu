@@ -1,6 +1,7 @@
 // C-ABI entry of kernel (3): dispatch between the batched shared-Gibbs-kernel solver and
 // the reference-form kernel (reference call site: pilotpy/tools/Trajectory.py:513-515).
 #include "sinkhorn.cuh"
+#include <cstdlib>
 
 namespace pilot {
 
@@ -10,10 +11,16 @@ struct SkWs {
     long long *redo;
 };
 
+// every slot of the panel kernel could in principle be handed over to the tail kernel
+static size_t sk_tail_slots() { return (size_t)sm_count() * skb_slots_per_cta(); }
+static size_t sk_tail_rec_bytes() { return (sk_tail_slots() * sizeof(SkTailRec) + 255) / 256 * 256; }
+static size_t sk_tail_uv_bytes(int KP) { return sk_tail_slots() * 2 * KP * sizeof(double); }
+
 static size_t sk_ws_bytes(int K)
 {
     const int KP = skb_pad(K <= 64 ? K : 64);
-    return 256 + skb_setup_bytes(KP) + skb_scratch_bytes(KP, sm_count()) + (size_t)SK_REDO_CAP * sizeof(long long);
+    return 256 + skb_setup_bytes(KP) + skb_scratch_bytes(KP, sm_count()) + (size_t)SK_REDO_CAP * sizeof(long long) +
+           sk_tail_rec_bytes() + sk_tail_uv_bytes(KP);
 }
 
 size_t sinkhorn_ws_bytes(int K) { return sk_ws_bytes(K); }
@@ -54,6 +61,14 @@ extern "C" int pilot_sinkhorn_pairs(const double *props, int S, int K, const dou
     ws.setup = (double *)(p + 256);
     ws.scratch = (double *)(p + 256 + skb_setup_bytes(KP));
     ws.redo = (long long *)(p + 256 + skb_setup_bytes(KP) + skb_scratch_bytes(KP, sm_count()));
+    unsigned char *ptail = (unsigned char *)ws.redo + (size_t)SK_REDO_CAP * sizeof(long long);
+    SkTail tail;
+    tail.rec = (SkTailRec *)ptail;
+    tail.uv = (double *)(ptail + sk_tail_rec_bytes());
+    tail.n_tail = ws.counter_fast + 3;
+    tail.evict_max = 2;
+    if (const char *e = getenv("PILOT_SK_EVICT")) tail.evict_max = atoi(e);  // experiments: 0 disables the hand-over
+    unsigned long long *tail_counter = ws.counter_fast + 4;
     bool symmetric = false;
     rc = skb_setup(cost, K, prm, ws.setup, &symmetric, st);
     if (rc) return rc;
@@ -75,8 +90,12 @@ extern "C" int pilot_sinkhorn_pairs(const double *props, int S, int K, const dou
         long long warp_cap = (pm.n_local + spw * ctas - 1) / (spw * ctas);
         if (warp_cap > skb_warps()) warp_cap = skb_warps();
         if (warp_cap < 1) warp_cap = 1;
-        rc = skb_launch(props, K, prm, pm, ws.setup, ws.scratch, (int)ctas, slot_cap, (int)warp_cap, symmetric, out,
-                        iters, absorptions, status, ws.counter_fast, ws.redo, ws.n_redo, st);
+        rc = skb_launch(props, K, prm, pm, ws.setup, ws.scratch, (int)ctas, slot_cap, (int)warp_cap, symmetric, tail,
+                        out, iters, absorptions, status, ws.counter_fast, ws.redo, ws.n_redo, st);
+        if (rc) return rc;
+        // the stragglers the panels handed over continue in warp form
+        rc = skt_launch(props, K, prm, pm, ws.setup, ws.scratch, symmetric, tail, tail_counter, out, iters,
+                        absorptions, status, ws.redo, ws.n_redo, st);
     } else {  // warp-specialised variant: same results, measured ~15 % slower, kept for A/B runs
         const long long sps = skw_slots_per_set();
         long long ctas = (pm.n_local + sps - 1) / sps;

@@ -11,6 +11,19 @@ struct SkParams {
 
 constexpr long long SK_REDO_CAP = 1LL << 20;
 
+// hand-over of straggler problems from the DMMA-panel kernel to the warp-form tail kernel
+struct SkTailRec {
+    long long prob;  // local problem index
+    int ii, nabs, hasabs;
+    int sslot;       // index of the problem's rea / reb block in the panel kernel's scratch
+};
+struct SkTail {
+    SkTailRec *rec;  // nullptr: no hand-over
+    double *uv;      // [slot][ut | vt][KP]
+    unsigned long long *n_tail;
+    int evict_max;   // a warp hands its problems over when the pool is empty and <= this many are left
+};
+
 size_t sinkhorn_ref_smem(int K);
 int sinkhorn_ref_launch(const double *props, int K, const double *cost, const SkParams &prm, const PairMap &pm,
                         const long long *list, const unsigned long long *n_list_dev, long long max_list,
@@ -26,8 +39,15 @@ int skb_slots_per_warp();
 int skb_warps();
 int skb_setup(const double *cost, int K, const SkParams &prm, double *setup, bool *symmetric, cudaStream_t st);
 int skb_launch(const double *props, int K, const SkParams &prm, const PairMap &pm, double *setup, double *scratch,
-               int ctas, int slot_cap, int warp_cap, bool symmetric, double *out, int *iters, int *absn, int *status,
-               unsigned long long *counter, long long *redo, unsigned long long *n_redo, cudaStream_t st);
+               int ctas, int slot_cap, int warp_cap, bool symmetric, const SkTail &tail, double *out, int *iters,
+               int *absn, int *status, unsigned long long *counter, long long *redo, unsigned long long *n_redo,
+               cudaStream_t st);
+
+// warp-form continuation of the handed-over problems (sinkhorn_tail.cu)
+int skt_launch(const double *props, int K, const SkParams &prm, const PairMap &pm, const double *setup,
+               const double *scratch, bool symmetric, const SkTail &tail, unsigned long long *tail_counter,
+               double *out, int *iters, int *absn, int *status, long long *redo, unsigned long long *n_redo,
+               cudaStream_t st);
 
 // warp-specialised variant (sinkhorn_ws.cu)
 size_t skw_smem_bytes(int KP);

@@ -101,7 +101,7 @@ sinkhorn_batched_kernel(const double *__restrict__ props, int K, SkParams prm, P
                         const double *__restrict__ gK0, const double *__restrict__ gK0T,
                         const double *__restrict__ gMK, const double *__restrict__ gc0,
                         double *__restrict__ scratch,  // [gridDim * WARPS * 8][2][KP] rea / reb
-                        double *__restrict__ out, int *__restrict__ iters_out, int *__restrict__ abs_out,
+                        SkTail tail, double *__restrict__ out, int *__restrict__ iters_out, int *__restrict__ abs_out,
                         int *__restrict__ status_out, unsigned long long *__restrict__ counter,
                         long long *__restrict__ redo_list, unsigned long long *__restrict__ n_redo)
 {
@@ -287,6 +287,42 @@ sinkhorn_batched_kernel(const double *__restrict__ props, int K, SkParams prm, P
         }
         __syncwarp();
 
+        // ---- tail hand-over: the pool is empty (some slot could not be refilled) and this warp is
+        // down to a few problems -- a DMMA panel at 1/8 .. 2/8 occupancy costs the stragglers ~6 us per
+        // iteration; the warp-form tail kernel continues them at ~0.5 us (state is clean here: the
+        // pending check / cap of every surviving slot has just been resolved) ----
+        if (tail.rec) {
+            const unsigned a0 = __ballot_sync(0xffffffffu, s_act[0]) & 0xfu;  // lanes 0..3: g == 0, t = 0..3
+            const unsigned a1 = __ballot_sync(0xffffffffu, s_act[1]) & 0xfu;
+            const int nact = __popc(a0) + __popc(a1);
+            if (nact > 0 && nact < SKB_SPW && nact <= tail.evict_max) {
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    unsigned mb = h ? a1 : a0;
+                    while (mb) {
+                        const int tt = __ffs(mb) - 1;
+                        mb &= mb - 1;
+                        const int col = 2 * tt + h;
+                        unsigned long long slot = 0;
+                        if (lane == 0) slot = atomicAdd(tail.n_tail, 1ULL);
+                        slot = __shfl_sync(0xffffffffu, slot, 0);
+                        double *dst = tail.uv + slot * 2 * KP;
+                        for (int r = lane; r < KP; r += 32) {
+                            dst[r] = U[r * PS + col];
+                            dst[KP + r] = V[r * PS + col];
+                        }
+                        if (t == tt && g == 0) {
+                            SkTailRec rec;
+                            rec.prob = sl[h]; rec.ii = s_ii[h]; rec.nabs = s_abs[h]; rec.hasabs = s_hasabs[h] ? 1 : 0;
+                            rec.sslot = (blockIdx.x * SKB_WARPS + warp) * SKB_SPW + col;
+                            tail.rec[slot] = rec;
+                        }
+                    }
+                }
+                break;
+            }
+        }
+
         // ---- v-update: Vt = b / T (my two slots are adjacent: one 128-bit store per row) ----
         long long mxv[2] = {0, 0};
         if (s_act[0] || s_act[1]) {
@@ -412,14 +448,15 @@ size_t skb_scratch_bytes(int KP, int ctas)
 {
     return sizeof(double) * (size_t)ctas * SKB_WARPS * SKB_SPW * 2 * KP;
 }
-int skb_pad(int K) { return K <= 16 ? 16 : (K <= 32 ? 32 : 64); }
+// padded problem size: the DMMA tiles need a multiple of 8, the work grows with KP^2
+int skb_pad(int K) { return K <= 16 ? 16 : (K <= 32 ? 32 : (K <= 48 ? 48 : 64)); }
 int skb_slots_per_cta() { return SKB_WARPS * SKB_SPW; }
 int skb_slots_per_warp() { return SKB_SPW; }
 int skb_warps() { return SKB_WARPS; }
 
 template <int KP, bool FULL, bool SYM>
 static int skb_launch_t(const double *props, int K, const SkParams &prm, const PairMap &pm, int slot_cap, int warp_cap,
-                        const double *setup, double *scratch, int ctas, double *out, int *iters, int *absn,
+                        const double *setup, double *scratch, const SkTail &tail, int ctas, double *out, int *iters, int *absn,
                         int *status, unsigned long long *counter, long long *redo, unsigned long long *n_redo,
                         cudaStream_t st)
 {
@@ -428,7 +465,8 @@ static int skb_launch_t(const double *props, int K, const SkParams &prm, const P
                                     (int)smem));
     const double *K0 = setup, *K0T = K0 + KP * KP, *MK = K0T + KP * KP, *c0 = MK + KP * KP;
     sinkhorn_batched_kernel<KP, FULL, SYM><<<ctas, SKB_WARPS * 32, smem, st>>>(
-        props, K, prm, pm, slot_cap, warp_cap, K0, K0T, MK, c0, scratch, out, iters, absn, status, counter, redo, n_redo);
+        props, K, prm, pm, slot_cap, warp_cap, K0, K0T, MK, c0, scratch, tail, out, iters, absn, status, counter, redo,
+        n_redo);
     PILOT_LAUNCH_CHECK();
     return 0;
 }
@@ -453,21 +491,23 @@ int skb_setup(const double *cost, int K, const SkParams &prm, double *setup, boo
 
 // `setup` must already hold the output of skb_setup
 int skb_launch(const double *props, int K, const SkParams &prm, const PairMap &pm, double *setup, double *scratch,
-               int ctas, int slot_cap, int warp_cap, bool symmetric, double *out, int *iters, int *absn, int *status,
-               unsigned long long *counter, long long *redo, unsigned long long *n_redo, cudaStream_t st)
+               int ctas, int slot_cap, int warp_cap, bool symmetric, const SkTail &tail, double *out, int *iters,
+               int *absn, int *status, unsigned long long *counter, long long *redo, unsigned long long *n_redo,
+               cudaStream_t st)
 {
     const int KP = skb_pad(K);
     const int h_asym = symmetric ? 0 : 1;
 #define SKB_GO(KPV, FULLV)                                                                                        \
     do {                                                                                                          \
         if (h_asym == 0)                                                                                          \
-            return skb_launch_t<KPV, FULLV, true>(props, K, prm, pm, slot_cap, warp_cap, setup, scratch, ctas, out, \
+            return skb_launch_t<KPV, FULLV, true>(props, K, prm, pm, slot_cap, warp_cap, setup, scratch, tail, ctas, out, \
                                                   iters, absn, status, counter, redo, n_redo, st);                 \
-        return skb_launch_t<KPV, FULLV, false>(props, K, prm, pm, slot_cap, warp_cap, setup, scratch, ctas, out,   \
+        return skb_launch_t<KPV, FULLV, false>(props, K, prm, pm, slot_cap, warp_cap, setup, scratch, tail, ctas, out,   \
                                                iters, absn, status, counter, redo, n_redo, st);                    \
     } while (0)
     if (KP == 16) { if (K == 16) SKB_GO(16, true); SKB_GO(16, false); }
     if (KP == 32) { if (K == 32) SKB_GO(32, true); SKB_GO(32, false); }
+    if (KP == 48) { if (K == 48) SKB_GO(48, true); SKB_GO(48, false); }
     if (K == 64) SKB_GO(64, true);
     SKB_GO(64, false);
 #undef SKB_GO

@@ -1,0 +1,258 @@
+// Kernel (3), tail of the DMMA-panel Sinkhorn solver: one warp per handed-over problem, continuing
+// from the exported scaled iterates (reference call site pilotpy/tools/Trajectory.py:513-515, POT
+// sinkhorn_stabilized schedule; same arithmetic as sinkhorn_warp.cu, K0 in shared memory because
+// 2 x 64 rows per lane do not fit the register file).
+//
+// A panel of 8 problems costs ~6 us per iteration however few of its slots are still in use; the
+// stragglers of a batch (the problems that run to the 1000-iteration cap while the mean is ~55)
+// would keep whole SMs busy at 1/8 occupancy for milliseconds.  Here lane j owns rows 2j and 2j + 1,
+// a matvec is 2 x KP DFMAs per lane against K0 columns read conflict-free from shared memory, and an
+// iteration takes ~0.5 us.
+#include "sinkhorn.cuh"
+
+namespace pilot {
+
+constexpr int SKT_WARPS = 16;
+
+__device__ __forceinline__ double skt_div(double x, double y)
+{
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(y));
+    const double e = fma(-y, r, 1.0);
+    const double q0 = x * r;
+    const double q = fma(q0, e, q0);
+    r = fma(r, e, r);
+    return fma(fma(-y, q, x), r, q);
+}
+
+// res[rr] = sum_i mat[i][row0 + rr] * buf[i]   (mat is [KP][KP], i-major; the lane's R rows are
+// adjacent, so R = 2 reads them with one 128-bit load; buf is broadcast as 128-bit loads)
+template <int KP, int R>
+__device__ __forceinline__ void skt_matvec(const double *__restrict__ mat, int row0, const double *buf,
+                                           double (&res)[R])
+{
+    // 8 independent chains per row: the dependent DFMA latency (~18 cycles), not the issue rate,
+    // bounds a lone warp
+    double s[R][8];
+#pragma unroll
+    for (int rr = 0; rr < R; ++rr)
+#pragma unroll
+        for (int c = 0; c < 8; ++c) s[rr][c] = 0.0;
+    const double *m = mat + row0;
+#pragma unroll 2
+    for (int i = 0; i < KP; i += 8) {
+        double xs[8];
+#pragma unroll
+        for (int c = 0; c < 8; c += 2) {
+            const double2 x = *reinterpret_cast<const double2 *>(buf + i + c);
+            xs[c] = x.x;
+            xs[c + 1] = x.y;
+        }
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+            if (R == 2) {
+                const double2 k = *reinterpret_cast<const double2 *>(m + (i + c) * KP);
+                s[0][c] = fma(k.x, xs[c], s[0][c]);
+                s[R - 1][c] = fma(k.y, xs[c], s[R - 1][c]);
+            } else {
+                s[0][c] = fma(m[(i + c) * KP], xs[c], s[0][c]);
+            }
+        }
+    }
+#pragma unroll
+    for (int rr = 0; rr < R; ++rr)
+        res[rr] = ((s[rr][0] + s[rr][1]) + (s[rr][2] + s[rr][3])) + ((s[rr][4] + s[rr][5]) + (s[rr][6] + s[rr][7]));
+}
+
+enum { SKT_PEND = 1, SKT_FORCE = 2, SKT_BAD = 4 };
+
+template <int KP, bool SYM>
+__global__ void __launch_bounds__(SKT_WARPS * 32, 1)
+sinkhorn_tail_kernel(const double *__restrict__ props, int K, SkParams prm, PairMap pm,
+                     const double *__restrict__ gK0, const double *__restrict__ gK0T,
+                     const double *__restrict__ gMK, const double *__restrict__ scratch, SkTail tail,
+                     unsigned long long *__restrict__ tail_counter, double *__restrict__ out,
+                     int *__restrict__ iters_out, int *__restrict__ abs_out, int *__restrict__ status_out,
+                     long long *__restrict__ redo_list, unsigned long long *__restrict__ n_redo)
+{
+    constexpr int R = (KP + 31) / 32;  // rows per lane
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    double *sK0 = reinterpret_cast<double *>(smem_raw);  // [i][j]: column access for T = K0^T ut
+    double *sMK = sK0 + KP * KP;                         // M o K0
+    double *sK0T = SYM ? sK0 : sMK + KP * KP;            // [j][i]: column access for S = K0 vt
+    double *sbuf = (SYM ? sMK : sK0T) + KP * KP;         // per warp: broadcast copies of ut, vt
+    const unsigned long long n_tail = *tail.n_tail;
+    if (n_tail == 0) return;
+    for (int e = threadIdx.x; e < KP * KP; e += blockDim.x) {
+        sK0[e] = gK0[e];
+        sMK[e] = gMK[e];
+        if (!SYM) sK0T[e] = gK0T[e];
+    }
+    __syncthreads();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    double *ub = sbuf + (size_t)warp * 2 * KP, *vb = ub + KP;
+    int row[R];
+    bool in_pad[R], row_ok[R];
+#pragma unroll
+    for (int rr = 0; rr < R; ++rr) {
+        const int r = R * lane + rr;  // adjacent rows per lane
+        in_pad[rr] = r < KP;
+        row_ok[rr] = r < K;
+        row[rr] = in_pad[rr] ? r : 0;
+    }
+    const unsigned long long tau_bits = (unsigned long long)__double_as_longlong(prm.tau);
+    const double invK = 1.0 / K;
+
+    for (;;) {
+        unsigned long long idx = 0;
+        if (lane == 0) idx = atomicAdd(tail_counter, 1ULL);
+        idx = __shfl_sync(0xffffffffu, idx, 0);
+        if (idx >= n_tail) break;
+        const SkTailRec rec = tail.rec[idx];
+        const long long w = rec.prob;
+        int si, sj;
+        global_to_ij(pm, local_to_global(pm, w), si, sj);
+        double a[R], b[R], u[R], v[R], rea[R], reb[R];
+#pragma unroll
+        for (int rr = 0; rr < R; ++rr) {
+            const int r = row[rr];
+            a[rr] = row_ok[rr] ? __ldg(props + (long long)si * K + r) : 0.0;
+            b[rr] = row_ok[rr] ? __ldg(props + (long long)sj * K + r) : 0.0;
+            u[rr] = row_ok[rr] ? tail.uv[idx * 2 * KP + r] : 0.0;
+            v[rr] = row_ok[rr] ? tail.uv[idx * 2 * KP + KP + r] : 0.0;
+            const bool ha = rec.hasabs && row_ok[rr];
+            rea[rr] = ha ? scratch[(size_t)rec.sslot * 2 * KP + r] : 1.0;
+            reb[rr] = ha ? scratch[(size_t)rec.sslot * 2 * KP + KP + r] : 1.0;
+        }
+        int ii = rec.ii, nabs = rec.nabs, status = PILOT_ST_MAXITER;
+        int ctl = 0;  // the hand-over happens right after a resolve: nothing pending
+        int until_check = (prm.check_every - ii % prm.check_every) % prm.check_every;
+        for (;;) {
+            // ---- T = K0^T ut, then resolve the check / cap of the previous iteration ----
+#pragma unroll
+            for (int rr = 0; rr < R; ++rr)
+                if (in_pad[rr]) ub[row[rr]] = u[rr];
+            __syncwarp();
+            double T[R];
+            skt_matvec<KP, R>(sK0, row[0], ub, T);
+            if (ctl) {
+                if (ctl & SKT_BAD) { status = -1; break; }
+                bool conv = false;
+                if (ctl & SKT_PEND) {
+                    double e2 = 0.0;
+#pragma unroll
+                    for (int rr = 0; rr < R; ++rr) {
+                        const double d = row_ok[rr] ? fma(v[rr], T[rr], -b[rr]) : 0.0;
+                        e2 = fma(d, d, e2);
+                    }
+                    conv = sqrt(warp_sum_d(e2)) <= prm.stop_thr;
+                }
+                if (conv) { status = PILOT_ST_CONVERGED; break; }
+                if (ctl & SKT_FORCE) { status = PILOT_ST_MAXITER; break; }
+            }
+            // ---- vt = b / T ----
+#pragma unroll
+            for (int rr = 0; rr < R; ++rr) {
+                v[rr] = row_ok[rr] ? skt_div(b[rr], T[rr]) : 0.0;
+                if (in_pad[rr]) vb[row[rr]] = v[rr];
+            }
+            __syncwarp();
+            // ---- ut = a / (K0 vt) ----
+            double S[R];
+            skt_matvec<KP, R>(sK0T, row[0], vb, S);
+            unsigned long long mx = 0;
+#pragma unroll
+            for (int rr = 0; rr < R; ++rr) {
+                u[rr] = row_ok[rr] ? skt_div(a[rr], S[rr]) : 0.0;
+                // u, v of the reference = ut * rea, vt * reb; NaN / Inf sort above every finite value
+                const unsigned long long bu = (unsigned long long)__double_as_longlong(u[rr] * rea[rr]);
+                const unsigned long long bv = (unsigned long long)__double_as_longlong(v[rr] * reb[rr]);
+                mx = max(mx, max(bu, bv));
+            }
+            ctl = (until_check == 0) ? SKT_PEND : 0;
+            until_check = (until_check == 0 ? prm.check_every : until_check) - 1;
+            ++ii;
+            if (ii >= prm.num_iter_max) ctl |= SKT_FORCE;
+            if (__any_sync(0xffffffffu, mx > tau_bits)) {
+                if (__any_sync(0xffffffffu, mx >= 0x7ff0000000000000ULL)) {
+                    ctl |= SKT_BAD;
+                } else {
+                    // absorption: u = v = 1/K in POT == divide the scaled iterates by K; remember 1/ut, 1/vt
+                    bool r = false;
+#pragma unroll
+                    for (int rr = 0; rr < R; ++rr)
+                        if (row_ok[rr]) {
+                            rea[rr] = 1.0 / u[rr];
+                            reb[rr] = 1.0 / v[rr];
+                            r |= !(u[rr] > 1e-250 && u[rr] < 1e250 && v[rr] > 1e-250 && v[rr] < 1e250);
+                            u[rr] *= invK;
+                            v[rr] *= invK;
+                        }
+                    ++nabs;
+                    if (__any_sync(0xffffffffu, r)) ctl |= SKT_BAD;
+                }
+            }
+        }
+        if (status >= 0) {
+            // cost = sum_j vt_j * sum_i (M o K0)_ij ut_i   (ub holds the current ut)
+            double W[R];
+            skt_matvec<KP, R>(sMK, row[0], ub, W);
+            double c = 0.0;
+#pragma unroll
+            for (int rr = 0; rr < R; ++rr) c = fma(v[rr], W[rr], c);
+            const double cost = warp_sum_d(c);
+            if (lane == 0) {
+                out[w] = cost;
+                if (iters_out) iters_out[w] = ii;
+                if (abs_out) abs_out[w] = nabs;
+                if (status_out) status_out[w] = status;
+            }
+        } else if (lane == 0) {
+            const unsigned long long slot = atomicAdd(n_redo, 1ULL);
+            if ((long long)slot < SK_REDO_CAP) redo_list[slot] = w;
+            out[w] = __longlong_as_double(0x7ff8000000000000LL);
+            if (status_out) status_out[w] = -1;
+        }
+        __syncwarp();
+    }
+}
+
+template <int KP, bool SYM>
+static int skt_launch_t(const double *props, int K, const SkParams &prm, const PairMap &pm, const double *setup,
+                        const double *scratch, const SkTail &tail, unsigned long long *tail_counter, double *out,
+                        int *iters, int *absn, int *status, long long *redo, unsigned long long *n_redo,
+                        cudaStream_t st)
+{
+    const size_t smem = sizeof(double) * ((size_t)(SYM ? 2 : 3) * KP * KP + (size_t)SKT_WARPS * 2 * KP);
+    PILOT_CUDA(cudaFuncSetAttribute(sinkhorn_tail_kernel<KP, SYM>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    (int)smem));
+    const double *K0 = setup, *K0T = K0 + KP * KP, *MK = K0T + KP * KP;
+    sinkhorn_tail_kernel<KP, SYM><<<sm_count(), SKT_WARPS * 32, smem, st>>>(
+        props, K, prm, pm, K0, K0T, MK, scratch, tail, tail_counter, out, iters, absn, status, redo, n_redo);
+    PILOT_LAUNCH_CHECK();
+    return 0;
+}
+
+// continues the problems the panel kernel handed over (none: the CTAs return at once)
+int skt_launch(const double *props, int K, const SkParams &prm, const PairMap &pm, const double *setup,
+               const double *scratch, bool symmetric, const SkTail &tail, unsigned long long *tail_counter,
+               double *out, int *iters, int *absn, int *status, long long *redo, unsigned long long *n_redo,
+               cudaStream_t st)
+{
+    const int KP = skb_pad(K);
+#define SKT_GO(KPV)                                                                                              \
+    do {                                                                                                         \
+        if (symmetric)                                                                                           \
+            return skt_launch_t<KPV, true>(props, K, prm, pm, setup, scratch, tail, tail_counter, out, iters,     \
+                                           absn, status, redo, n_redo, st);                                      \
+        return skt_launch_t<KPV, false>(props, K, prm, pm, setup, scratch, tail, tail_counter, out, iters, absn,  \
+                                        status, redo, n_redo, st);                                               \
+    } while (0)
+    if (KP == 16) SKT_GO(16);
+    if (KP == 32) SKT_GO(32);
+    if (KP == 48) SKT_GO(48);
+    SKT_GO(64);
+#undef SKT_GO
+}
+
+}  // namespace pilot

@@ -477,6 +477,7 @@ int skw_launch(const double *props, int K, const SkParams &prm, const PairMap &p
     } while (0)
     if (KP == 16) { if (K == 16) SKW_GO(16, true); SKW_GO(16, false); }
     if (KP == 32) { if (K == 32) SKW_GO(32, true); SKW_GO(32, false); }
+    if (KP == 48) { if (K == 48) SKW_GO(48, true); SKW_GO(48, false); }
     if (K == 64) SKW_GO(64, true);
     SKW_GO(64, false);
 #undef SKW_GO
