@@ -429,7 +429,9 @@ def run_b200(args):
     if world > 1:
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
     t_e2e = te.item()
-    h2d = n * 8 + X.nbytes + (k + s) * 4
+    # embedding + the two label-code columns (categorical obs: int8 codes for < 128 categories, else int16/32)
+    code_bytes = sum(1 if c < 128 else (2 if c < 32768 else 4) for c in (k, s))
+    h2d = n * code_bytes + X.nbytes + (k + s) * 4
     d2h = s * s * 8 + s * k * 8 + k * k * 8 + (k + s) * 8
 
     if rank != 0:

@@ -76,15 +76,20 @@ def extract_data_anno_pathomics_from_h5ad(adata, var_names=[], clusters_col="Cel
 # ---------------------------------------------------------------------------
 def _raw_codes(col: pd.Series) -> Tuple[np.ndarray, object]:
     """Integer codes of a label column without hashing when it is Categorical.
-    Returns (int32 codes, labels-by-code).  Missing labels are an error."""
+    Returns (codes, labels-by-code); the codes keep the narrow dtype pandas stores them in (int8 for
+    < 128 categories: 1 MB instead of 4 MB per million cells over PCIe) and are widened on the device.
+    Missing labels are an error."""
     if isinstance(col.dtype, pd.CategoricalDtype):
         codes = col.cat.codes.to_numpy()
         labels = col.cat.categories
     else:
         codes, labels = pd.factorize(col, sort=False)
+        codes = codes.astype(np.int32, copy=False)
     if len(codes) and codes.min() < 0:
         raise ValueError(f"column {col.name!r} contains missing labels")
-    return np.ascontiguousarray(codes, dtype=np.int32), labels
+    if codes.dtype not in (np.int8, np.int16, np.int32):
+        codes = codes.astype(np.int32)
+    return np.ascontiguousarray(codes), labels
 
 
 def _unique_in_order(col: pd.Series, labels, perm: np.ndarray):
@@ -108,18 +113,54 @@ def _to_device(arr: np.ndarray) -> torch.Tensor:
     return torch.from_numpy(arr).to(_device(), non_blocking=False)
 
 
+# Host staging.  A pageable source makes cudaMemcpy stage through the driver's bounce buffer and block
+# the host; label codes therefore go through a grow-only pinned buffer of our own and are copied
+# asynchronously.  The buffer is reused by the next call, which is safe because every public function
+# ends with a device-to-host read of its result (a full stream sync).
+_pinned_stage = {"buf": None, "used": 0}
+_copy_streams: Dict[int, "torch.cuda.Stream"] = {}
+
+
+def _stage_reset() -> None:
+    _pinned_stage["used"] = 0
+
+
+def _to_device_staged(arr: np.ndarray) -> torch.Tensor:
+    dev = _device()
+    nbytes = (arr.nbytes + 255) // 256 * 256
+    off = _pinned_stage["used"]
+    buf = _pinned_stage["buf"]
+    if buf is None or off + nbytes > buf.numel():
+        if off != 0:  # would have to move live data: plain blocking copy instead
+            return _to_device(arr)
+        buf = torch.empty(max(nbytes * 2, 1 << 22), dtype=torch.uint8, pin_memory=True)
+        _pinned_stage["buf"] = buf
+    _pinned_stage["used"] = off + nbytes
+    host = buf[off:off + arr.nbytes].view(torch.from_numpy(arr).dtype).view(arr.shape)
+    host.numpy()[...] = arr
+    return host.to(dev, non_blocking=True)
+
+
+def _copy_stream(dev: torch.device) -> "torch.cuda.Stream":
+    idx = dev.index if dev.index is not None else torch.cuda.current_device()
+    if idx not in _copy_streams:
+        _copy_streams[idx] = torch.cuda.Stream(device=dev)
+    return _copy_streams[idx]
+
+
 class _Labels:
     """Device-resident factorised annotation shared by the stages of one call."""
 
     def __init__(self, annot: pd.DataFrame, cell_col_name, sample_col_name):
+        _stage_reset()  # previous calls ended with a sync: their staged copies are done
         self.n = len(annot)
         self.cell_col = annot[cell_col_name]
         self.samp_col = annot[sample_col_name]
         ct, self.ct_labels = _raw_codes(self.cell_col)
         sm, self.sm_labels = _raw_codes(self.samp_col)
         self.K_raw, self.S_raw = len(self.ct_labels), len(self.sm_labels)
-        self.ct_dev = _to_device(ct)
-        self.sm_dev = _to_device(sm)
+        self.ct_dev = _to_device_staged(ct).to(torch.int32)
+        self.sm_dev = _to_device_staged(sm).to(torch.int32)
         self.counts_raw, first_ct, first_smp = ops.hist(self.ct_dev, self.sm_dev, self.K_raw, self.S_raw)
         first = torch.cat([first_ct, first_smp]).cpu().numpy()  # the only sync of stage 1
         fk, fs = first[: self.K_raw], first[self.K_raw:]
@@ -140,6 +181,10 @@ class _Labels:
 
 
 def _embedding_to_device(data) -> torch.Tensor:
+    """Stage the embedding.  Page-locked input (e.g. a torch pinned tensor's numpy view) is copied on a
+    side stream so that the label factorisation, the histogram and the proportion table -- host work
+    plus small kernels -- run while the 200 MB cross PCIe; the compute stream waits for the copy before
+    it is first read (stage 2).  Pageable input is a plain blocking copy."""
     X = data.to_numpy() if isinstance(data, pd.DataFrame) else np.asarray(data)
     if X.dtype not in (np.float32, np.float64):
         X = X.astype(np.float64)  # pandas' nanmedian promotes non-float input to float64
@@ -147,7 +192,20 @@ def _embedding_to_device(data) -> torch.Tensor:
         raise ValueError("embedding must be 2-dimensional")
     if not X.flags.c_contiguous:
         X = np.ascontiguousarray(X)
-    return _to_device(X)
+    host = torch.from_numpy(X)
+    if not host.is_pinned():
+        return _to_device(X)
+    dev = _device()
+    main = torch.cuda.current_stream(dev)
+    side = _copy_stream(dev)
+    X_dev = torch.empty(host.shape, dtype=host.dtype, device=dev)  # allocated in compute-stream order
+    side.wait_stream(main)
+    with torch.cuda.stream(side):
+        X_dev.copy_(host, non_blocking=True)
+    done = torch.cuda.Event()
+    done.record(side)
+    X_dev._pilot_ready = done  # consumed by _cost_device
+    return X_dev
 
 
 def _props_dict(samples, props_host: np.ndarray) -> Dict[object, np.ndarray]:
@@ -204,6 +262,9 @@ def Cluster_Representations(df, cell_col=0, sample_col=1, regulizer=0.2, normali
 def _cost_device(lab: _Labels, X_dev: torch.Tensor, metric) -> Tuple[torch.Tensor, torch.Tensor]:
     if X_dev.shape[0] != lab.n:
         raise ValueError(f"Item wrong length {lab.n} instead of {X_dev.shape[0]}.")
+    ready = getattr(X_dev, "_pilot_ready", None)
+    if ready is not None:
+        torch.cuda.current_stream(X_dev.device).wait_event(ready)
     _, cent64_raw = ops.centroid_median(X_dev, lab.ct_dev, lab.K_raw)
     cent64 = cent64_raw.index_select(0, lab.perm_k_dev.long()).contiguous()
     cost, cost_norm, _ = ops.cdist(cent64, metric)
@@ -270,19 +331,22 @@ def wasserstein_distance(adata, emb_matrix="X_PCA", clusters_col="cell_types", s
                          return_sil_ari=False):
     """Drop-in for ``pilotpy.tl.wasserstein_distance``: writes ``data``, ``annot``,
     ``proportions``, ``cost``, ``EMD_df``, ``EMD`` and ``real_labels`` into ``adata.uns``."""
+    X_dev = None
     if data_type == "scRNA":
+        # stage the embedding straight from the caller's array (no detour through the DataFrame) and
+        # first of all: the copy overlaps everything up to the median kernel
+        X_dev = _embedding_to_device(adata.obsm[emb_matrix])
         data, annot = extract_data_anno_scRNA_from_h5ad(adata, emb_matrix=emb_matrix, clusters_col=clusters_col,
                                                         sample_col=sample_col, status=status)
     else:
         data, annot = extract_data_anno_pathomics_from_h5ad(adata, var_names=list(adata.var_names),
                                                             clusters_col=clusters_col, sample_col=sample_col,
                                                             status=status)
+        X_dev = _embedding_to_device(data)
     adata.uns["data"] = data
     adata.uns["annot"] = annot
 
     lab = _Labels(annot, "cell_type", "sampleID")
-    # stage the embedding straight from the caller's array (no detour through the DataFrame)
-    X_dev = _embedding_to_device(adata.obsm[emb_matrix] if data_type == "scRNA" else data)
     props, counts = lab.proportions(regulizer, normalization)
     cost, cost_norm = _cost_device(lab, X_dev, metric)
     props_h = props.cpu().numpy()
