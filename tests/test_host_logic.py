@@ -81,3 +81,27 @@ def test_extract_mirrors_reference_columns(tmp_path):
     assert os.path.isdir("Results_PILOT/plots")
     with pytest.raises(KeyError):
         tl.extract_data_anno_scRNA_from_h5ad(adata, emb_matrix="missing")
+
+
+@pytest.mark.parametrize("kind", ["categorical", "object", "int", "str", "mixed"])
+def test_labelled_frames_equal_the_reference_statements(kind):
+    """_cost_frame / _emd_frame build the frame in one step; it must be what the reference's
+    from_dict / columns / new column / set_index statements (Trajectory.py:470-473, 518-521) build."""
+    import pandas as pd
+    from pilot_b200 import tl
+    K = 7
+    rng = np.random.default_rng(0)
+    mat = rng.random((K, K))
+    names = [f"ct{i}" for i in range(K)]
+    labels = {"categorical": pd.Categorical.from_codes(rng.permutation(K), categories=names),
+              "object": np.array(names, dtype=object), "int": np.arange(K) * 3,
+              "str": pd.array(names, dtype="str") if hasattr(pd, "StringDtype") else np.array(names, dtype=object),
+              "mixed": np.array([1, "a", 2.5, "b", 3, "c", None], dtype=object)}[kind]
+    for name, build in (("cell_types", tl._cost_frame), ("sampleID", tl._emd_frame)):
+        lab = list(labels) if name == "sampleID" else labels
+        want = tl._labelled_square_reference(mat, lab, name)
+        got = build(mat, lab)
+        pd.testing.assert_frame_equal(got, want, check_exact=True, check_index_type=True, check_column_type=True)
+        assert type(got.index) is type(want.index) and type(got.columns) is type(want.columns)
+        assert got.index.name == want.index.name and got.columns.name == want.columns.name
+        np.testing.assert_array_equal(got.to_numpy(), mat.T)
