@@ -95,7 +95,10 @@ __device__ __forceinline__ long long abs_bits(double x) { return __double_as_lon
 // wavefronts per load, the minimum (an 8-column swizzle on odd rows gave 4).
 __device__ __forceinline__ int swz(int row, int col) { return col ^ ((row & 3) << 2); }
 
-template <int KP, bool FULL, bool SYM>
+// KP: storage extent (row stride of K0, panel rows; 16, 32, 48 or 64).  KC <= KP: compute extent, the
+// multiple of 8 that covers K -- the DMMA tiles beyond it would only multiply zeros (K = 40: 25 instead
+// of 36 tile products per k-step pair).
+template <int KP, int KC, bool FULL, bool SYM>
 __global__ void __launch_bounds__(SKB_WARPS * 32, 1)
 sinkhorn_batched_kernel(const double *__restrict__ props, int K, SkParams prm, PairMap pm, int slot_cap, int warp_cap,
                         const double *__restrict__ gK0, const double *__restrict__ gK0T,
@@ -105,8 +108,8 @@ sinkhorn_batched_kernel(const double *__restrict__ props, int K, SkParams prm, P
                         int *__restrict__ status_out, unsigned long long *__restrict__ counter,
                         long long *__restrict__ redo_list, unsigned long long *__restrict__ n_redo)
 {
-    constexpr int MT = KP / 8;   // accumulator row tiles
-    constexpr int KS = KP / 4;   // k-steps of 4
+    constexpr int MT = KC / 8;   // accumulator row tiles
+    constexpr int KS = KC / 4;   // k-steps of 4
     constexpr int PS = SKB_SPW;  // panel row stride (doubles): 64-byte rows, conflict-free as they are
     extern __shared__ __align__(16) unsigned char smem_raw[];
     // symmetric cost (always so in PILOT: squareform(pdist)): K0^T == K0, and the second matrix slot
@@ -249,7 +252,7 @@ sinkhorn_batched_kernel(const double *__restrict__ props, int K, SkParams prm, P
                 if (stt >= 0) {
                     // cost = sum_j Vt_j * sum_i (M o K0)_ij Ut_i ; lane = column j
                     const double *mk = sym ? sSecond : gMK;
-                    for (int j = lane; j < KP; j += 32) {
+                    for (int j = lane; j < KC; j += 32) {  // panel rows >= KC are never written
                         double w0 = 0.0, w1 = 0.0;
                         for (int i = 0; i + 1 < K; i += 2) {
                             w0 = fma(mk[i * KP + j], U[i * PS + col], w0);
@@ -307,7 +310,7 @@ sinkhorn_batched_kernel(const double *__restrict__ props, int K, SkParams prm, P
                         if (lane == 0) slot = atomicAdd(tail.n_tail, 1ULL);
                         slot = __shfl_sync(0xffffffffu, slot, 0);
                         double *dst = tail.uv + slot * 2 * KP;
-                        for (int r = lane; r < KP; r += 32) {
+                        for (int r = lane; r < KC; r += 32) {
                             dst[r] = U[r * PS + col];
                             dst[KP + r] = V[r * PS + col];
                         }
@@ -454,17 +457,17 @@ int skb_slots_per_cta() { return SKB_WARPS * SKB_SPW; }
 int skb_slots_per_warp() { return SKB_SPW; }
 int skb_warps() { return SKB_WARPS; }
 
-template <int KP, bool FULL, bool SYM>
+template <int KP, int KC, bool FULL, bool SYM>
 static int skb_launch_t(const double *props, int K, const SkParams &prm, const PairMap &pm, int slot_cap, int warp_cap,
                         const double *setup, double *scratch, const SkTail &tail, int ctas, double *out, int *iters, int *absn,
                         int *status, unsigned long long *counter, long long *redo, unsigned long long *n_redo,
                         cudaStream_t st)
 {
     const size_t smem = skb_smem_bytes(KP);
-    PILOT_CUDA(cudaFuncSetAttribute(sinkhorn_batched_kernel<KP, FULL, SYM>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    PILOT_CUDA(cudaFuncSetAttribute(sinkhorn_batched_kernel<KP, KC, FULL, SYM>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                     (int)smem));
     const double *K0 = setup, *K0T = K0 + KP * KP, *MK = K0T + KP * KP, *c0 = MK + KP * KP;
-    sinkhorn_batched_kernel<KP, FULL, SYM><<<ctas, SKB_WARPS * 32, smem, st>>>(
+    sinkhorn_batched_kernel<KP, KC, FULL, SYM><<<ctas, SKB_WARPS * 32, smem, st>>>(
         props, K, prm, pm, slot_cap, warp_cap, K0, K0T, MK, c0, scratch, tail, out, iters, absn, status, counter, redo,
         n_redo);
     PILOT_LAUNCH_CHECK();
@@ -497,19 +500,27 @@ int skb_launch(const double *props, int K, const SkParams &prm, const PairMap &p
 {
     const int KP = skb_pad(K);
     const int h_asym = symmetric ? 0 : 1;
-#define SKB_GO(KPV, FULLV)                                                                                        \
+#define SKB_GO(KPV, KCV)                                                                                          \
     do {                                                                                                          \
-        if (h_asym == 0)                                                                                          \
-            return skb_launch_t<KPV, FULLV, true>(props, K, prm, pm, slot_cap, warp_cap, setup, scratch, tail, ctas, out, \
-                                                  iters, absn, status, counter, redo, n_redo, st);                 \
-        return skb_launch_t<KPV, FULLV, false>(props, K, prm, pm, slot_cap, warp_cap, setup, scratch, tail, ctas, out,   \
-                                               iters, absn, status, counter, redo, n_redo, st);                    \
+        if (h_asym == 0) {                                                                                        \
+            if (K == KCV)                                                                                         \
+                return skb_launch_t<KPV, KCV, true, true>(props, K, prm, pm, slot_cap, warp_cap, setup, scratch,   \
+                                                          tail, ctas, out, iters, absn, status, counter, redo,     \
+                                                          n_redo, st);                                             \
+            return skb_launch_t<KPV, KCV, false, true>(props, K, prm, pm, slot_cap, warp_cap, setup, scratch, tail, \
+                                                       ctas, out, iters, absn, status, counter, redo, n_redo, st); \
+        }                                                                                                         \
+        if (K == KCV)                                                                                             \
+            return skb_launch_t<KPV, KCV, true, false>(props, K, prm, pm, slot_cap, warp_cap, setup, scratch, tail, \
+                                                       ctas, out, iters, absn, status, counter, redo, n_redo, st); \
+        return skb_launch_t<KPV, KCV, false, false>(props, K, prm, pm, slot_cap, warp_cap, setup, scratch, tail,   \
+                                                    ctas, out, iters, absn, status, counter, redo, n_redo, st);    \
     } while (0)
-    if (KP == 16) { if (K == 16) SKB_GO(16, true); SKB_GO(16, false); }
-    if (KP == 32) { if (K == 32) SKB_GO(32, true); SKB_GO(32, false); }
-    if (KP == 48) { if (K == 48) SKB_GO(48, true); SKB_GO(48, false); }
-    if (K == 64) SKB_GO(64, true);
-    SKB_GO(64, false);
+    if (KP == 16) SKB_GO(16, 16);
+    if (KP == 32) { if (K <= 24) SKB_GO(32, 24); SKB_GO(32, 32); }
+    if (KP == 48) { if (K <= 40) SKB_GO(48, 40); SKB_GO(48, 48); }
+    if (K <= 56) SKB_GO(64, 56);
+    SKB_GO(64, 64);
 #undef SKB_GO
 }
 

@@ -75,7 +75,7 @@ def test_emd_nonmetric_cost_and_counts():
     np.testing.assert_allclose(got, want, rtol=EMD_RTOL, atol=1e-12)
 
 
-@pytest.mark.parametrize("K,reg", [(10, 0.1), (30, 0.1), (64, 0.1), (64, 0.01), (40, 0.02), (5, 0.5), (30, 0.01), (32, 0.02), (16, 0.05), (48, 0.1), (33, 0.05)])
+@pytest.mark.parametrize("K,reg", [(10, 0.1), (30, 0.1), (64, 0.1), (64, 0.01), (40, 0.02), (5, 0.5), (30, 0.01), (32, 0.02), (16, 0.05), (48, 0.1), (33, 0.05), (20, 0.1), (56, 0.1), (50, 0.05)])
 @pytest.mark.parametrize("algo", [0, 1, 2, 3])
 def test_sinkhorn_pairs_match_oracle(K, reg, algo):
     S = 12 if reg < 0.05 else 20
