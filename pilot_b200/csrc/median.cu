@@ -234,6 +234,7 @@ constexpr int MS_PROC = 4;              // tile processors (64 threads) per stre
 constexpr int MS_MAXCH = 4;             // column chunks of 64 per processor -> D <= 256
 constexpr int MS_STAGE_BYTES = 32768;   // candidates staged in shared memory by the finish kernel
 constexpr int MS_MAXITEMS_PER_TYPE = 2048;
+constexpr int MS_FIN_THREADS = 256;
 
 // shared-memory reduction without the compiler's warp-aggregation collective
 __device__ __forceinline__ void red_shared_inc(unsigned int *p)
@@ -472,9 +473,10 @@ template <int BYTES> __device__ __forceinline__ void cp_async_bytes(unsigned sme
 
 // The streaming pass.  A tile processor (64 threads) takes work items = (type, <= item_rows rows of
 // that type); rows are gathered with cp.async into a double-buffered shared-memory tile (each row is
-// one contiguous D-element read), then THREAD = COLUMN: the pivots of (type, d) and the five
-// counters live in registers, elements strictly inside the bracket go to the thread's private list.
-// No atomics, no ballots, no tables: ~10 instructions per element.
+// one contiguous D-element read), then THREAD = COLUMN: the pivots of (type, d) and three counters
+// (below, above, listed) live in registers; everything inside the closed bracket, and every NaN,
+// goes to the thread's private list through a predicated store.  No atomics, no ballots, no tables,
+// two compares per element.
 template <typename T, int VB>  // VB = bytes per cp.async (row starts and D * sizeof(T) are multiples of it)
 __global__ void __launch_bounds__(MS_PROC * 64)
 msort_stream_kernel(const T *__restrict__ X, int D, long long ldx, int TR, MsWs<T> ws)
@@ -497,13 +499,13 @@ msort_stream_kernel(const T *__restrict__ X, int D, long long ldx, int TR, MsWs<
         const int k = ws.item_k[it];
         const unsigned r0 = ws.item_r0[it], r1 = ws.item_r1[it];
         T lo[MS_MAXCH], hi[MS_MAXCH];
-        unsigned c_below[MS_MAXCH], c_eqlo[MS_MAXCH], c_eqhi[MS_MAXCH], c_nan[MS_MAXCH], c_cand[MS_MAXCH];
+        unsigned c_below[MS_MAXCH], c_above[MS_MAXCH], c_cand[MS_MAXCH];
 #pragma unroll
         for (int ch = 0; ch < MS_MAXCH; ++ch) {
             const int d = ch * 64 + ptid;
             lo[ch] = d < D ? ws.piv[2 * ((size_t)k * D + d)] : (T)0;
             hi[ch] = d < D ? ws.piv[2 * ((size_t)k * D + d) + 1] : (T)0;
-            c_below[ch] = c_eqlo[ch] = c_eqhi[ch] = c_nan[ch] = c_cand[ch] = 0u;
+            c_below[ch] = c_above[ch] = c_cand[ch] = 0u;
         }
         const int ntiles = (int)((r1 - r0 + TR - 1) / TR);
         auto load_tile = [&](int t, int buf) {
@@ -537,22 +539,23 @@ msort_stream_kernel(const T *__restrict__ X, int D, long long ldx, int TR, MsWs<
                 if (d < D) {
                     T *cl = ws.cand + ((size_t)it * D + d) * capi;
                     const T l = lo[ch], h = hi[ch];
-                    const bool hneql = h != l;
-                    unsigned nb = c_below[ch], ne = c_eqlo[ch], nh = c_eqhi[ch], nn = c_nan[ch], nc = c_cand[ch];
+                    // lo == hi: the sample saw a plateau of ties -- they are counted (everything that is
+                    // neither below nor above nor stored), not stored; x != NaN is true for every x
+                    const T tie = l == h ? l : (T)NAN;
+                    unsigned nb = c_below[ch], na = c_above[ch], nc = c_cand[ch];
                     const T *col = src + d;
 #pragma unroll 4
                     for (int row = 0; row < rows; ++row) {
                         const T x = col[row * D];
-                        nb += x < l ? 1u : 0u;
-                        ne += x == l ? 1u : 0u;
-                        nh += (x == h && hneql) ? 1u : 0u;
-                        nn += x != x ? 1u : 0u;
-                        if (x > l && x < h) {
-                            if (nc < capi) cl[nc] = x;
-                            ++nc;
-                        }
+                        const bool lt = x < l, gt = x > h;
+                        nb += lt ? 1u : 0u;
+                        na += gt ? 1u : 0u;
+                        // the closed bracket [lo, hi] and every NaN go to the list
+                        const bool st = !lt && !gt && x != tie;
+                        if (st && nc < capi) cl[nc] = x;
+                        nc += st ? 1u : 0u;
                     }
-                    c_below[ch] = nb; c_eqlo[ch] = ne; c_eqhi[ch] = nh; c_nan[ch] = nn; c_cand[ch] = nc;
+                    c_below[ch] = nb; c_above[ch] = na; c_cand[ch] = nc;
                 }
             }
             asm volatile("bar.sync %0, 64;" ::"r"(proc + 1) : "memory");  // tile buffer free again
@@ -562,16 +565,17 @@ msort_stream_kernel(const T *__restrict__ X, int D, long long ldx, int TR, MsWs<
             const int d = ch * 64 + ptid;
             if (d < D) {
                 unsigned int *o = ws.cnt + ((size_t)it * D + d) * 5;
-                o[0] = c_below[ch]; o[1] = c_eqlo[ch]; o[2] = c_eqhi[ch]; o[3] = c_nan[ch]; o[4] = c_cand[ch];
+                o[0] = c_below[ch]; o[1] = c_above[ch]; o[4] = c_cand[ch];
             }
         }
     }
 }
 
-// one CTA per (type, dim): rank bookkeeping over the type's items, selection inside the candidates,
-// exact fallback over the type's own rows when the bracket missed or a list overflowed
+// one CTA per (type, dim): rank bookkeeping over the type's items (below / tie plateau / lists /
+// above), NaN count and selection inside the lists, exact fallback over the type's own rows when the
+// bracket missed or a list overflowed
 template <typename T>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(MS_FIN_THREADS)
 msort_finish_kernel(const T *__restrict__ X, int D, long long ldx, MsWs<T> ws, T *__restrict__ cent,
                     double *__restrict__ cent64)
 {
@@ -593,16 +597,16 @@ msort_finish_kernel(const T *__restrict__ X, int D, long long ldx, MsWs<T> ws, T
     if (threadIdx.x == 0) s_over = nit > MS_MAXITEMS_PER_TYPE ? 1 : 0;
     __syncthreads();
     {
-        unsigned long long a[4] = {0, 0, 0, 0};
+        unsigned long long a[2] = {0, 0};
         for (int q = threadIdx.x; q < nit; q += blockDim.x) {
             const unsigned int *c = ws.cnt + ((size_t)(i0 + q) * D + d) * 5;
-            a[0] += c[0]; a[1] += c[1]; a[2] += c[2]; a[3] += c[3];
+            a[0] += c[0]; a[1] += c[1];
             const unsigned nc = c[4];
             if (nc > ws.capi) s_over = 1;
             if (q < MS_MAXITEMS_PER_TYPE) s_off[q + 1] = nc < ws.capi ? nc : ws.capi;
         }
 #pragma unroll
-        for (int j = 0; j < 4; ++j) atomicAdd(&s_sum[j], a[j]);
+        for (int j = 0; j < 2; ++j) atomicAdd(&s_sum[j], a[j]);
     }
     __syncthreads();
     if (threadIdx.x < 32) {
@@ -624,67 +628,95 @@ msort_finish_kernel(const T *__restrict__ X, int D, long long ldx, MsWs<T> ws, T
     }
     __syncthreads();
     const bool overflow = s_over != 0;
-    const long long below = (long long)s_sum[0], eq_lo = (long long)s_sum[1], eq_hi = (long long)s_sum[2];
-    const long long n_nan = (long long)s_sum[3], nmid = (long long)s_sum[4];
+    const long long below = (long long)s_sum[0], above = (long long)s_sum[1], nlist = (long long)s_sum[4];
     const unsigned toff = ws.type_off[k];
     const long long Nk = (long long)ws.type_off[k + 1] - toff;
+    const T lo = ws.piv[2 * kd], hi = ws.piv[2 * kd + 1];
+    // the lists hold the closed bracket [lo, hi] and every NaN; with lo == hi the ties were counted
+    // instead of listed: ties = Nk - below - above - listed
+    const long long ties = lo == hi ? Nk - below - above - nlist : 0;
+    const bool staged = !overflow && nlist <= STAGE;
+    if (staged) {
+        // warp w copies the lists of items w, w + 8, ... (each a short contiguous run)
+        const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+        for (int q = warp; q < nit; q += MS_FIN_THREADS / 32) {
+            const T *cl = ws.cand + ((size_t)(i0 + q) * D + d) * ws.capi;
+            const unsigned o = s_off[q], c = s_off[q + 1] - o;
+            for (unsigned i = lane; i < c; i += 32) s_stage[o + i] = cl[i];
+        }
+        __syncthreads();
+    }
+    // every list element, NaN included
+    auto lst_all = [&](auto f) {
+        if (staged) {
+            for (unsigned i = threadIdx.x; i < (unsigned)nlist; i += blockDim.x) f(s_stage[i]);
+        } else {
+            for (int q = 0; q < nit; ++q) {
+                const T *cl = ws.cand + ((size_t)(i0 + q) * D + d) * ws.capi;
+                const unsigned c = s_off[q + 1] - s_off[q];
+                for (unsigned i = threadIdx.x; i < c; i += blockDim.x) f(cl[i]);
+            }
+        }
+    };
+    long long n_nan = 0;
+    if (!overflow) {
+        unsigned my = 0;
+        lst_all([&](T x) { my += x != x ? 1u : 0u; });
+        if (my) atomicAdd(&s_sum[3], (unsigned long long)my);
+        __syncthreads();
+        n_nan = (long long)s_sum[3];
+    }
+    const long long nmid = nlist - n_nan;  // listed, orderable
     const long long nvalid = Nk - n_nan;
     T med;
-    if (nvalid <= 0) {
+    if (nvalid <= 0 && !overflow) {
         med = (T)NAN;
     } else {
         const long long r0 = (nvalid - 1) / 2, r1 = nvalid / 2;
-        const T lo = ws.piv[2 * kd], hi = ws.piv[2 * kd + 1];
-        // where does each rank land?  0: < lo (fail) 1: == lo 2: candidates 3: == hi 4: beyond (fail)
+        // where does each rank land?  0: < lo (fail) 1: the tie plateau lo == hi 2: the lists 4: beyond (fail)
         auto region = [&](long long r, long long &rin) -> int {
             if (r < below) return 0;
             r -= below;
-            if (r < eq_lo) return 1;
-            r -= eq_lo;
+            if (r < ties) return 1;
+            r -= ties;
             if (r < nmid) { rin = r; return 2; }
-            r -= nmid;
-            if (r < eq_hi) return 3;
             return 4;
         };
         long long j0 = 0, j1 = 0;
-        const int g0 = region(r0, j0), g1 = region(r1, j1);
+        const int g0 = overflow ? 0 : region(r0, j0), g1 = overflow ? 0 : region(r1, j1);
         T v0, v1;
         if (overflow || g0 == 0 || g0 == 4 || g1 == 0 || g1 == 4) {
             // exact fallback: radix select over this type's own rows
             if (threadIdx.x == 0) atomicAdd(&ws.hdr->fail, 1u);
-            auto col = [&](auto f) {
+            __shared__ unsigned long long s_valid;
+            if (threadIdx.x == 0) s_valid = 0ULL;
+            __syncthreads();
+            {
+                unsigned long long my = 0;
                 for (long long i = threadIdx.x; i < Nk; i += blockDim.x) {
                     const T x = X[(long long)ws.sorted_rows[toff + i] * ldx + d];
-                    if (x == x) f(x);
+                    my += x == x ? 1ULL : 0ULL;
                 }
-            };
-            cta_select2_raw<T>(col, r0, r1, hist, sh, (Key)0, BITS - 8, v0, v1);
+                if (my) atomicAdd(&s_valid, my);
+            }
+            __syncthreads();
+            const long long nv = (long long)s_valid;
+            if (nv <= 0) {
+                v0 = v1 = (T)NAN;
+            } else {
+                auto col = [&](auto f) {
+                    for (long long i = threadIdx.x; i < Nk; i += blockDim.x) {
+                        const T x = X[(long long)ws.sorted_rows[toff + i] * ldx + d];
+                        if (x == x) f(x);
+                    }
+                };
+                cta_select2_raw<T>(col, (nv - 1) / 2, nv / 2, hist, sh, (Key)0, BITS - 8, v0, v1);
+            }
         } else {
             T m0 = lo, m1 = lo;
             if (g0 == 2 || g1 == 2) {
-                const bool staged = nmid <= STAGE;
-                if (staged) {
-                    // warp w copies the lists of items w, w + 4, ... (each a short contiguous run)
-                    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-                    for (int q = warp; q < nit; q += 4) {
-                        const T *cl = ws.cand + ((size_t)(i0 + q) * D + d) * ws.capi;
-                        const unsigned o = s_off[q], c = s_off[q + 1] - o;
-                        for (unsigned i = lane; i < c; i += 32) s_stage[o + i] = cl[i];
-                    }
-                    __syncthreads();
-                }
-                auto lst = [&](auto f) {
-                    if (staged) {
-                        for (unsigned i = threadIdx.x; i < (unsigned)nmid; i += blockDim.x) f(s_stage[i]);
-                    } else {
-                        for (int q = 0; q < nit; ++q) {
-                            const T *cl = ws.cand + ((size_t)(i0 + q) * D + d) * ws.capi;
-                            const unsigned c = s_off[q + 1] - s_off[q];
-                            for (unsigned i = threadIdx.x; i < c; i += blockDim.x) f(cl[i]);
-                        }
-                    }
-                };
-                // every candidate lies strictly between lo and hi: the digits above the first one in
+                auto lst = [&](auto f) { lst_all([&](T x) { if (x == x) f(x); }); };
+                // every orderable list element lies in [lo, hi]: the digits above the first one in
                 // which key(lo) and key(hi) differ are common to all of them
                 Key prefix = 0;
                 int first = BITS - 8;
@@ -695,8 +727,8 @@ msort_finish_kernel(const T *__restrict__ X, int D, long long ldx, MsWs<T> ws, T
                 }
                 cta_select2_raw<T>(lst, g0 == 2 ? j0 : 0, g1 == 2 ? j1 : 0, hist, sh, prefix, first, m0, m1);
             }
-            v0 = g0 == 1 ? lo : (g0 == 3 ? hi : m0);
-            v1 = g1 == 1 ? lo : (g1 == 3 ? hi : m1);
+            v0 = g0 == 1 ? lo : m0;
+            v1 = g1 == 1 ? lo : m1;
         }
         if (v0 == v1) med = v0;
         else if (sizeof(T) == 4) med = (T)__fdiv_rn(__fadd_rn((float)v0, (float)v1), 2.0f);
@@ -806,7 +838,7 @@ static int median_run_sorted(const T *X, long long n, int D, long long ldx, cons
 #undef MS_LAUNCH
         PILOT_LAUNCH_CHECK();
     }
-    msort_finish_kernel<T><<<(unsigned)kd, 128, 0, st>>>(X, D, ldx, ws, cent, cent64);
+    msort_finish_kernel<T><<<(unsigned)kd, MS_FIN_THREADS, 0, st>>>(X, D, ldx, ws, cent, cent64);
     PILOT_LAUNCH_CHECK();
     return 0;
 }
