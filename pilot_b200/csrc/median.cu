@@ -605,8 +605,13 @@ msort_finish_kernel(const T *__restrict__ X, int D, long long ldx, MsWs<T> ws, T
             if (nc > ws.capi) s_over = 1;
             if (q < MS_MAXITEMS_PER_TYPE) s_off[q + 1] = nc < ws.capi ? nc : ws.capi;
         }
+        // one shared 64-bit atomic per warp (they are CAS loops: 256 contending threads would serialise)
 #pragma unroll
-        for (int j = 0; j < 2; ++j) atomicAdd(&s_sum[j], a[j]);
+        for (int j = 0; j < 2; ++j) {
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) a[j] += __shfl_xor_sync(0xffffffffu, a[j], o);
+            if ((threadIdx.x & 31) == 0 && a[j]) atomicAdd(&s_sum[j], a[j]);
+        }
     }
     __syncthreads();
     if (threadIdx.x < 32) {
@@ -639,10 +644,28 @@ msort_finish_kernel(const T *__restrict__ X, int D, long long ldx, MsWs<T> ws, T
     if (staged) {
         // warp w copies the lists of items w, w + 8, ... (each a short contiguous run)
         const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-        for (int q = warp; q < nit; q += MS_FIN_THREADS / 32) {
-            const T *cl = ws.cand + ((size_t)(i0 + q) * D + d) * ws.capi;
-            const unsigned o = s_off[q], c = s_off[q + 1] - o;
-            for (unsigned i = lane; i < c; i += 32) s_stage[o + i] = cl[i];
+        // four lists per round, so that four independent global loads are in flight per lane
+        constexpr int NW = MS_FIN_THREADS / 32;
+        for (int q = warp; q < nit; q += 4 * NW) {
+            const T *cl[4];
+            unsigned o[4], c[4], cmax = 0;
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int qq = q + u * NW;
+                const bool ok = qq < nit;
+                cl[u] = ws.cand + ((size_t)(i0 + (ok ? qq : q)) * D + d) * ws.capi;
+                o[u] = ok ? s_off[qq] : 0u;
+                c[u] = ok ? s_off[qq + 1] - o[u] : 0u;
+                cmax = c[u] > cmax ? c[u] : cmax;
+            }
+            for (unsigned i = lane; i < cmax; i += 32) {
+                T v[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) v[u] = i < c[u] ? cl[u][i] : (T)0;
+#pragma unroll
+                for (int u = 0; u < 4; ++u)
+                    if (i < c[u]) s_stage[o[u] + i] = v[u];
+            }
         }
         __syncthreads();
     }
