@@ -57,14 +57,18 @@ __global__ void skb_setup_kernel(const double *__restrict__ M, int K, int KP, do
         K0T[j * KP + i] = k0;
         MK[i * KP + j] = mk;
     }
-    if (blockIdx.x == 0)
-        for (int j = threadIdx.x; j < KP; j += blockDim.x) {
-            double s = 0.0;
-            const double u0 = 1.0 / K;
-            if (j < K)
-                for (int i = 0; i < K; ++i) s += exp(-M[i * K + j] / reg) * u0;
-            c0[j] = s;
-        }
+    // c0_j = sum_i K0_ij / K: one warp per column, the exps in parallel (a serial loop of K double-precision
+    // exps per thread made this the longest part of the kernel)
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    const int nwarps = (gridDim.x * blockDim.x) >> 5;
+    for (int j = warp; j < KP; j += nwarps) {
+        double s = 0.0;
+        const double u0 = 1.0 / K;
+        if (j < K)
+            for (int i = lane; i < K; i += 32) s += exp(-M[i * K + j] / reg) * u0;
+        s = warp_sum_d(s);
+        if (lane == 0) c0[j] = s;
+    }
 }
 
 __device__ __forceinline__ void dmma884(double &c0, double &c1, double a, double b)
