@@ -15,20 +15,20 @@ namespace pilot {
 
 constexpr int SWK_WARPS = 8;
 
-// branch-free x / y for finite positive y: 20-bit seed, one Newton step on the reciprocal and the
-// quotient side by side (40 bits), one residual correction -- a dependent chain of MUFU + 4 FP64 ops
+// branch-free x / y for finite positive y: 20-bit seed r, e = 1 - y r, q = x r (1 + e + e^2): relative
+// error e^3 ~ 2^-60 before the final rounding, a dependent chain of MUFU + 3 FP64 ops (the chain
+// length, not the op count, is what a lone warp pays for)
 __device__ __forceinline__ double swk_div(double x, double y)
 {
     double r;
     asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(y));
     const double e = fma(-y, r, 1.0);
     const double q0 = x * r;
-    const double q = fma(q0, e, q0);
-    r = fma(r, e, r);
-    return fma(fma(-y, q, x), r, q);
+    return fma(q0, fma(e, e, e), q0);
 }
 
-// sum_i k0[i] * buf[i]; buf is read as 128-bit broadcasts, eight independent chains
+// sum_i k0[i] * buf[i]; buf is read as 128-bit broadcasts; 8 independent chains of KP / 8 FMAs and a
+// 3-level tree (16 chains would save one more dependent op but spill at KP = 32)
 template <int KP>
 __device__ __forceinline__ double swk_matvec(const double (&k0)[KP], const double *buf)
 {
