@@ -1,7 +1,6 @@
 // C-ABI entry of kernel (3): dispatch between the batched shared-Gibbs-kernel solver and
 // the reference-form kernel (reference call site: pilotpy/tools/Trajectory.py:513-515).
 #include "sinkhorn.cuh"
-#include <cstdlib>
 
 namespace pilot {
 
@@ -66,8 +65,7 @@ extern "C" int pilot_sinkhorn_pairs(const double *props, int S, int K, const dou
     tail.rec = (SkTailRec *)ptail;
     tail.uv = (double *)(ptail + sk_tail_rec_bytes());
     tail.n_tail = ws.counter_fast + 3;
-    tail.evict_max = 2;
-    if (const char *e = getenv("PILOT_SK_EVICT")) tail.evict_max = atoi(e);  // experiments: 0 disables the hand-over
+    tail.evict_max = 2;  // measured: 0 (no hand-over) 2.23 ms, 2: 1.45 ms, 4: 1.44 ms, 7: 1.56 ms for 10^4 problems at K = 64
     unsigned long long *tail_counter = ws.counter_fast + 4;
     bool symmetric = false;
     rc = skb_setup(cost, K, prm, ws.setup, &symmetric, st);
