@@ -134,11 +134,17 @@ int pilot_cdist(const double *centroids_f64, int K, int D, int metric,
  * iters / absorptions / status may be NULL.
  * algo: 0 = shared-Gibbs-kernel solvers (fast path: one warp per problem with K0
  *           in registers for K <= 32 and a symmetric cost, else 8-problem DMMA
- *           panels; problems they cannot represent are re-solved by the
- *           reference-form kernel),
+ *           panels whose stragglers are finished by a warp-form tail kernel;
+ *           problems the scaled form cannot represent are re-solved by the
+ *           reference-form kernel).  Which problems migrate to the tail kernel
+ *           depends on timing, so two calls agree to rounding (<= 1e-12
+ *           relative), not bit for bit; iteration counts are reproducible,
  *       1 = reference-form kernel only (per-problem Gibbs kernel, literal schedule),
  *       2 = warp-specialised variant of the DMMA-panel solver (kept for A/B measurements),
- *       3 = DMMA-panel solver for every K <= 64.
+ *       3 = DMMA-panel solver (+ tail) for every K <= 64.
+ * K > 64 (up to ~150) always takes the reference-form kernel.  The call contains
+ * one 4-byte device-to-host read (is the cost symmetric?) and is otherwise
+ * asynchronous on `stream`.
  */
 int pilot_sinkhorn_pairs(const double *props, int S, int K, const double *cost,
                          double reg, int num_iter_max, double stop_thr,
