@@ -245,9 +245,12 @@ class DeviceStep:
 
 # kernel launches of ONE DeviceStep.run() (my kernels only; memsets and torch's index_select excluded):
 # hist_init + hist (2), prior + finalize (2), median count + plan + scatter + pivot + stream + finish (6),
-# cdist prep/pair/norm (3), sinkhorn setup + solver + reference-form redo (3) or emd (1), unpack (1)
-def launches_per_step(reg):
-    return 2 + 2 + 6 + 3 + (3 if reg is not None else 1) + 1
+# cdist prep/pair/norm (3), unpack (1) and the pair stage: emd (1), or Sinkhorn setup + reference-form redo (2) +
+# for K <= 32 the warp solver + the general panel and tail variants that return at once when the cost is
+# symmetric (3), else both variants of the panel and of the tail kernel (4)
+def launches_per_step(reg, k=30):
+    pair = 1 if reg is None else (2 + (3 if k <= 32 else 4))
+    return 2 + 2 + 6 + 3 + pair + 1
 
 
 def pair_kernel_slices(peak_fp64):
@@ -453,7 +456,7 @@ def run_b200(args):
             "e2e": {"value": s * s / t_e2e, "unit": UNIT, "h2d_bytes_per_step": int(h2d),
                     "d2h_bytes_per_step": int(d2h), "ms_per_step": t_e2e * 1e3,
                     "api": "pilot_b200.tl.wasserstein_distance(adata) with categorical obs and a pinned host embedding"},
-            "gpu_launches": launches_per_step(reg) * args.steps,
+            "gpu_launches": launches_per_step(reg, k) * args.steps,
             "stage_ms": stage_ms, "roofline": roofline}
 
     line["pipe_peaks"] = peaks

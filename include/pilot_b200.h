@@ -138,13 +138,13 @@ int pilot_cdist(const double *centroids_f64, int K, int D, int metric,
  *           problems the scaled form cannot represent are re-solved by the
  *           reference-form kernel).  Which problems migrate to the tail kernel
  *           depends on timing, so two calls agree to rounding (<= 1e-12
- *           relative), not bit for bit; iteration counts are reproducible,
+ *           relative), not bit for bit,
  *       1 = reference-form kernel only (per-problem Gibbs kernel, literal schedule),
  *       2 = warp-specialised variant of the DMMA-panel solver (kept for A/B measurements),
  *       3 = DMMA-panel solver (+ tail) for every K <= 64.
- * K > 64 (up to ~150) always takes the reference-form kernel.  The call contains
- * one 4-byte device-to-host read (is the cost symmetric?) and is otherwise
- * asynchronous on `stream`.
+ * K > 64 (up to ~150) always takes the reference-form kernel.  The call is fully
+ * asynchronous on `stream` (whether the cost is symmetric is decided on the
+ * device: both variants of a solver are enqueued, one returns at once).
  */
 int pilot_sinkhorn_pairs(const double *props, int S, int K, const double *cost,
                          double reg, int num_iter_max, double stop_thr,

@@ -67,9 +67,12 @@ extern "C" int pilot_sinkhorn_pairs(const double *props, int S, int K, const dou
     tail.n_tail = ws.counter_fast + 3;
     tail.evict_max = 2;  // measured: 0 (no hand-over) 2.23 ms, 2: 1.45 ms, 4: 1.44 ms, 7: 1.56 ms for 10^4 problems at K = 64
     unsigned long long *tail_counter = ws.counter_fast + 4;
-    bool symmetric = false;
-    rc = skb_setup(cost, K, prm, ws.setup, &symmetric, st);
+    rc = skb_setup(cost, K, prm, ws.setup, st);
     if (rc) return rc;
+    // The cost is symmetric in PILOT (a pdist matrix) but the API takes any matrix.  Whether it is is known
+    // only on the device (setup kernel), so the symmetric and the general variant of each solver are both
+    // enqueued and the one that does not apply returns at once: no host read-back, the call is fully
+    // asynchronous on `stream`.
     // persistent grid: one CTA per SM.  With little work (latency-, not throughput-bound) spread it
     // over all SMs and run only as many warps / slot sets per CTA as there are slot-loads of
     // problems: fewer of them share the FP64 tensor pipe, so every iteration returns sooner.
@@ -77,32 +80,42 @@ extern "C" int pilot_sinkhorn_pairs(const double *props, int S, int K, const dou
     // few cell types: one warp per problem with K0 in registers (lowest latency per iteration, and
     // for 17..32 types also the higher throughput).  With <= 16 types half of its lanes idle, so a
     // large batch goes to the DMMA panels instead (measured: 400 K problems, K = 12: 5.6 vs 6.9 ms).
-    const bool warp_form = algo == 0 && symmetric && K <= swk_max_k() && (K > 16 || pm.n_local < 200000);
-    if (warp_form) {
+    const bool warp_form = algo == 0 && K <= swk_max_k() && (K > 16 || pm.n_local < 200000);
+    if (warp_form) {  // symmetric cost only; an asymmetric one falls through to the general panels below
         rc = swk_launch(props, K, prm, pm, ws.setup, out, iters, absorptions, status, ws.counter_fast, ws.redo,
                         ws.n_redo, st);
-    } else if (algo != 2) {
+        if (rc) return rc;
+    }
+    if (algo != 2) {
         const long long spw = skb_slots_per_warp();
         long long ctas = (pm.n_local + spw - 1) / spw;
         if (ctas > sm_count()) ctas = sm_count();
         long long warp_cap = (pm.n_local + spw * ctas - 1) / (spw * ctas);
         if (warp_cap > skb_warps()) warp_cap = skb_warps();
         if (warp_cap < 1) warp_cap = 1;
-        rc = skb_launch(props, K, prm, pm, ws.setup, ws.scratch, (int)ctas, slot_cap, (int)warp_cap, symmetric, tail,
-                        out, iters, absorptions, status, ws.counter_fast, ws.redo, ws.n_redo, st);
-        if (rc) return rc;
+        for (int sym = warp_form ? 0 : 1; sym >= 0; --sym) {
+            rc = skb_launch(props, K, prm, pm, ws.setup, ws.scratch, (int)ctas, slot_cap, (int)warp_cap, sym != 0,
+                            tail, out, iters, absorptions, status, ws.counter_fast, ws.redo, ws.n_redo, st);
+            if (rc) return rc;
+        }
         // the stragglers the panels handed over continue in warp form
-        rc = skt_launch(props, K, prm, pm, ws.setup, ws.scratch, symmetric, tail, tail_counter, out, iters,
-                        absorptions, status, ws.redo, ws.n_redo, st);
-    } else {  // warp-specialised variant: same results, measured ~15 % slower (DESIGN.md 4.3), kept for A/B runs
+        for (int sym = warp_form ? 0 : 1; sym >= 0; --sym) {
+            rc = skt_launch(props, K, prm, pm, ws.setup, ws.scratch, sym != 0, tail, tail_counter, out, iters,
+                            absorptions, status, ws.redo, ws.n_redo, st);
+            if (rc) return rc;
+        }
+    } else {  // warp-specialised variant: same results, measured ~15 % slower (DESIGN.md 2.4), kept for A/B runs
         const long long sps = skw_slots_per_set();
         long long ctas = (pm.n_local + sps - 1) / sps;
         if (ctas > sm_count()) ctas = sm_count();
         long long set_cap = (pm.n_local + sps * ctas - 1) / (sps * ctas);
         if (set_cap > skw_sets()) set_cap = skw_sets();
         if (set_cap < 1) set_cap = 1;
-        rc = skw_launch(props, K, prm, pm, ws.setup, ws.scratch, (int)ctas, slot_cap, (int)set_cap, symmetric, out,
-                        iters, absorptions, status, ws.counter_fast, ws.redo, ws.n_redo, st);
+        for (int sym = 1; sym >= 0; --sym) {
+            rc = skw_launch(props, K, prm, pm, ws.setup, ws.scratch, (int)ctas, slot_cap, (int)set_cap, sym != 0, out,
+                            iters, absorptions, status, ws.counter_fast, ws.redo, ws.n_redo, st);
+            if (rc) return rc;
+        }
     }
     if (rc) return rc;
     // problems the scaled form could not represent (normally none): reference-form kernel

@@ -37,7 +37,7 @@ size_t skb_scratch_bytes(int KP, int ctas);
 int skb_slots_per_cta();
 int skb_slots_per_warp();
 int skb_warps();
-int skb_setup(const double *cost, int K, const SkParams &prm, double *setup, bool *symmetric, cudaStream_t st);
+int skb_setup(const double *cost, int K, const SkParams &prm, double *setup, cudaStream_t st);
 int skb_launch(const double *props, int K, const SkParams &prm, const PairMap &pm, double *setup, double *scratch,
                int ctas, int slot_cap, int warp_cap, bool symmetric, const SkTail &tail, double *out, int *iters,
                int *absn, int *status, unsigned long long *counter, long long *redo, unsigned long long *n_redo,

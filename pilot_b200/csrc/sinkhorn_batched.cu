@@ -113,6 +113,9 @@ sinkhorn_batched_kernel(const double *__restrict__ props, int K, SkParams prm, P
                         int *__restrict__ status_out, unsigned long long *__restrict__ counter,
                         long long *__restrict__ redo_list, unsigned long long *__restrict__ n_redo)
 {
+    // the symmetric and the general variant are both enqueued; the flag the setup kernel left behind the
+    // c0 vector decides on the device which one runs (no host read-back in a Sinkhorn call)
+    if ((reinterpret_cast<const int *>(gc0 + KP)[0] != 0) == SYM) return;
     constexpr int MT = KC / 8;   // accumulator row tiles
     constexpr int KS = KC / 4;   // k-steps of 4
     constexpr int PS = SKB_SPW;  // panel row stride (doubles): 64-byte rows, conflict-free as they are
@@ -479,21 +482,15 @@ static int skb_launch_t(const double *props, int K, const SkParams &prm, const P
     return 0;
 }
 
-// computes K0, K0^T, M o K0, c0 and reports whether the cost is symmetric (the PILOT case), which
-// selects the variant that keeps M o K0 in shared memory; the flag comes back through one 4-byte
-// read-back, the only host sync of a Sinkhorn call
-int skb_setup(const double *cost, int K, const SkParams &prm, double *setup, bool *symmetric, cudaStream_t st)
+// computes K0, K0^T, M o K0, c0 and the asymmetry flag (an int behind c0: != 0 when M differs from its
+// transpose); the solver kernels read the flag themselves
+int skb_setup(const double *cost, int K, const SkParams &prm, double *setup, cudaStream_t st)
 {
     const int KP = skb_pad(K);
     PILOT_CUDA(cudaMemsetAsync(setup + 3 * KP * KP + KP, 0, sizeof(double), st));
     skb_setup_kernel<<<8, 256, 0, st>>>(cost, K, KP, prm.reg, setup, setup + KP * KP, setup + 2 * KP * KP,
                                         setup + 3 * KP * KP, reinterpret_cast<int *>(setup + 3 * KP * KP + KP));
     PILOT_LAUNCH_CHECK();
-    int h_asym = 1;
-    PILOT_CUDA(cudaMemcpyAsync(&h_asym, reinterpret_cast<int *>(setup + 3 * KP * KP + KP), sizeof(int),
-                               cudaMemcpyDeviceToHost, st));
-    PILOT_CUDA(cudaStreamSynchronize(st));
-    *symmetric = h_asym == 0;
     return 0;
 }
 

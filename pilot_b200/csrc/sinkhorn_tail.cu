@@ -70,7 +70,8 @@ template <int KP, bool SYM>
 __global__ void __launch_bounds__(SKT_WARPS * 32, 1)
 sinkhorn_tail_kernel(const double *__restrict__ props, int K, SkParams prm, PairMap pm,
                      const double *__restrict__ gK0, const double *__restrict__ gK0T,
-                     const double *__restrict__ gMK, const double *__restrict__ scratch, SkTail tail,
+                     const double *__restrict__ gMK, const int *__restrict__ asym_flag,
+                     const double *__restrict__ scratch, SkTail tail,
                      unsigned long long *__restrict__ tail_counter, double *__restrict__ out,
                      int *__restrict__ iters_out, int *__restrict__ abs_out, int *__restrict__ status_out,
                      long long *__restrict__ redo_list, unsigned long long *__restrict__ n_redo)
@@ -82,7 +83,7 @@ sinkhorn_tail_kernel(const double *__restrict__ props, int K, SkParams prm, Pair
     double *sK0T = SYM ? sK0 : sMK + KP * KP;            // [j][i]: column access for S = K0 vt
     double *sbuf = (SYM ? sMK : sK0T) + KP * KP;         // per warp: broadcast copies of ut, vt
     const unsigned long long n_tail = *tail.n_tail;
-    if (n_tail == 0) return;
+    if (n_tail == 0 || (*asym_flag != 0) == SYM) return;
     for (int e = threadIdx.x; e < KP * KP; e += blockDim.x) {
         sK0[e] = gK0[e];
         sMK[e] = gMK[e];
@@ -227,8 +228,9 @@ static int skt_launch_t(const double *props, int K, const SkParams &prm, const P
     PILOT_CUDA(cudaFuncSetAttribute(sinkhorn_tail_kernel<KP, SYM>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                     (int)smem));
     const double *K0 = setup, *K0T = K0 + KP * KP, *MK = K0T + KP * KP;
+    const int *asym = reinterpret_cast<const int *>(setup + 3 * KP * KP + KP);
     sinkhorn_tail_kernel<KP, SYM><<<sm_count(), SKT_WARPS * 32, smem, st>>>(
-        props, K, prm, pm, K0, K0T, MK, scratch, tail, tail_counter, out, iters, absn, status, redo, n_redo);
+        props, K, prm, pm, K0, K0T, MK, asym, scratch, tail, tail_counter, out, iters, absn, status, redo, n_redo);
     PILOT_LAUNCH_CHECK();
     return 0;
 }

@@ -50,12 +50,13 @@ template <int KP>
 __global__ void __launch_bounds__(SWK_WARPS * 32, 2)
 sinkhorn_warp_kernel(const double *__restrict__ props, int K, SkParams prm, PairMap pm,
                      const double *__restrict__ gK0, const double *__restrict__ gMK,
-                     double *__restrict__ out, int *__restrict__ iters_out, int *__restrict__ abs_out,
+                     const int *__restrict__ asym_flag, double *__restrict__ out, int *__restrict__ iters_out, int *__restrict__ abs_out,
                      int *__restrict__ status_out, unsigned long long *__restrict__ counter,
                      long long *__restrict__ redo_list, unsigned long long *__restrict__ n_redo)
 {
     __shared__ double sMK[KP * KP];                             // M o K0, for the final cost
     __shared__ __align__(16) double sbuf[SWK_WARPS][2][KP];    // per warp: broadcast copies of ut, vt
+    if (*asym_flag != 0) return;  // asymmetric cost: the panel kernel enqueued behind this one runs instead
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     for (int e = threadIdx.x; e < KP * KP; e += blockDim.x) sMK[e] = gMK[e];
     __syncthreads();
@@ -170,13 +171,14 @@ int swk_launch(const double *props, int K, const SkParams &prm, const PairMap &p
 {
     const int KP = skb_pad(K);
     const double *K0 = setup, *MK = setup + 2 * KP * KP;
+    const int *asym = reinterpret_cast<const int *>(setup + 3 * KP * KP + KP);
     long long ctas = pm.n_local;  // spread a small batch over all SMs, one problem per warp at a time
     if (ctas > 2LL * sm_count()) ctas = 2LL * sm_count();
     if (KP == 16)
-        sinkhorn_warp_kernel<16><<<(int)ctas, SWK_WARPS * 32, 0, st>>>(props, K, prm, pm, K0, MK, out, iters, absn,
+        sinkhorn_warp_kernel<16><<<(int)ctas, SWK_WARPS * 32, 0, st>>>(props, K, prm, pm, K0, MK, asym, out, iters, absn,
                                                                        status, counter, redo, n_redo);
     else
-        sinkhorn_warp_kernel<32><<<(int)ctas, SWK_WARPS * 32, 0, st>>>(props, K, prm, pm, K0, MK, out, iters, absn,
+        sinkhorn_warp_kernel<32><<<(int)ctas, SWK_WARPS * 32, 0, st>>>(props, K, prm, pm, K0, MK, asym, out, iters, absn,
                                                                        status, counter, redo, n_redo);
     PILOT_LAUNCH_CHECK();
     return 0;

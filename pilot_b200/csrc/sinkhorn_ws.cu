@@ -63,6 +63,7 @@ sinkhorn_ws_kernel(const double *__restrict__ props, int K, SkParams prm, PairMa
                    int *__restrict__ status_out, unsigned long long *__restrict__ counter,
                    long long *__restrict__ redo_list, unsigned long long *__restrict__ n_redo)
 {
+    if ((reinterpret_cast<const int *>(gc0 + KP)[0] != 0) == SYM) return;  // see sinkhorn_batched.cu
     constexpr int MT = KP / 8;   // accumulator row tiles
     constexpr int KS = KP / 4;   // k-steps of 4
     constexpr int PS = SKW_SPW;  // panel row stride (doubles)
