@@ -401,7 +401,10 @@ def run_b200(args):
         kern = "sinkhorn_warp_kernel" if k <= 32 else "sinkhorn_batched_kernel"
         roofline = {"kernel": kern + " (all-pairs stage incl. setup/unpack)", "bound": "tensor",
                     "achieved": ach, "peak": peaks["fp64_dmma_tflops"], "unit": "TFLOP/s",
-                    "frac": ach / peaks["fp64_dmma_tflops"], "traffic": None,
+                    "frac": ach / peaks["fp64_dmma_tflops"],
+                    # dram__bytes_read.sum + dram__bytes_write.sum of one ncu --set full capture of this kernel at the
+                    # C2 pair stage (profiles/sinkhorn_warp_r1.txt): the inputs are 24 KB of proportions and a 7 KB cost
+                    "traffic": 62720 if (k <= 32 and args.workload == "c2") else None,
                     "peak_source": "FP64 mma.sync peak measured in this run by pilot_pipe_peak (MEASURED_PEAKS.json "
                                    "holds only bf16 and HBM peaks)",
                     "algorithmic_flops": flops, "mean_iters": mean_iters, "max_iters": max_iters,

@@ -366,12 +366,14 @@ def wasserstein_distance(adata, emb_matrix="X_PCA", clusters_col="cell_types", s
     lab = _Labels(annot, "cell_type", "sampleID")
     props, counts = lab.proportions(regulizer, normalization)
     cost, cost_norm = _cost_device(lab, X_dev, metric)
+    # enqueue the pair stage before the first device-to-host read, so that the host-side checks and the
+    # construction of the result containers overlap it (its result is dropped if a check raises)
+    emd_dev = pairs.all_pairs(props, cost_norm, regularized, reg)
     props_h = props.cpu().numpy()
     if int(counts.sum().item()) != lab.n:
         raise ValueError("label codes out of range")
     if regularized == "unreg":
         _check_emd_inputs(props_h, np.empty((lab.K, lab.K)))
-    emd_dev = pairs.all_pairs(props, cost_norm, regularized, reg)
 
     adata.uns["proportions"] = _props_dict(lab.samples, props_h)
     dis = cost.cpu().numpy()
