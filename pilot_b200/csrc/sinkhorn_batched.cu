@@ -275,6 +275,7 @@ sinkhorn_batched_kernel(const double *__restrict__ props, int K, SkParams prm, P
                 if (lane == 0) w = atomicAdd(counter, 1ULL);
                 w = __shfl_sync(0xffffffffu, w, 0);
                 const bool mine = t == tt;
+                __syncwarp();  // every lane has read the slot's U, V columns before its owners refill them
                 if (mine && g == 0) {
                     if (stt >= 0) {
                         out[sl[h]] = cost;
