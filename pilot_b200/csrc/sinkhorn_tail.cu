@@ -6,8 +6,9 @@
 // A panel of 8 problems costs ~6 us per iteration however few of its slots are still in use; the
 // stragglers of a batch (the problems that run to the 1000-iteration cap while the mean is ~55)
 // would keep whole SMs busy at 1/8 occupancy for milliseconds.  Here lane j owns rows 2j and 2j + 1,
-// a matvec is 2 x KP DFMAs per lane against K0 columns read conflict-free from shared memory, and an
-// iteration takes ~0.5 us.
+// a matvec is 2 x KP DFMAs per lane against K0 columns read conflict-free from shared memory (128-bit
+// loads), and an iteration takes 1.2 us at K = 64 -- bound by the ~45 B/clk one warp gets out of its SM
+// sub-partition's shared-memory port, not by the arithmetic.
 #include "sinkhorn.cuh"
 
 namespace pilot {
