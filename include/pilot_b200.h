@@ -27,9 +27,10 @@
 extern "C" {
 #endif
 
-#define PILOT_B200_ABI_VERSION 1
+#define PILOT_B200_ABI_VERSION 2
 
-/* element types of the embedding handed to pilot_centroid_median */
+/* element types of the embedding handed to pilot_centroid_median; also the `precision`
+ * of the two pair solvers (FP64 = the 1e-9 parity tier, FP32 = the 1e-4 tier) */
 #define PILOT_F32 0
 #define PILOT_F64 1
 
@@ -57,18 +58,21 @@ extern "C" {
 #define PILOT_WS_EMD      2
 
 /*
- * Partition of the linear pair space [0, total) over `nranks` processes:
- * blocks of `block` consecutive problems are dealt round-robin; rank r owns
- * blocks r, r+nranks, ...  Its packed output holds its blocks back to back.
- * nranks=1, rank=0 means "everything".  
+ * Partition of the window [first, first + total) of the linear pair space over
+ * `nranks` processes: blocks of `block` consecutive problems are dealt
+ * round-robin; rank r owns blocks r, r+nranks, ...  Its packed output holds its
+ * blocks back to back.  nranks=1, rank=0, first=0 means "everything".  A window
+ * (first > 0) lets the host solve, gather and copy out the matrix band by band.
+ * 
  */
 typedef struct {
-    int64_t total;   /* S*S (FULL) or S*(S-1)/2 (UPPER), or fewer to truncate */
+    int64_t total;   /* problems in the window: first + total <= S*S (FULL) or S*(S-1)/2 (UPPER) */
     int64_t block;   /* problems per block (>=1) */
     int32_t nranks;
     int32_t rank;
     int32_t mode;    /* PILOT_PAIRS_* */
     int32_t reserved;
+    int64_t first;   /* linear index of the window's first problem */
 } pilot_pair_range;
 
 int         pilot_abi_version(void);
@@ -76,6 +80,8 @@ const char *pilot_last_error(void);
 /* number of problems `range` assigns to range->rank */
 int64_t     pilot_range_count(const pilot_pair_range *range);
 size_t      pilot_workspace_bytes(int kind, int64_t n, int K, int S, int D);
+/* kernels this library has launched in this process so far (bench.py's gpu_launches) */
+uint64_t    pilot_launch_count(void);
 
 /*
  * (1) Proportion counting -- replaces the pandas unique/value_counts/boolean-mask
@@ -136,32 +142,36 @@ int pilot_cdist(const double *centroids_f64, int K, int D, int metric,
  *           in registers for K <= 32 and a symmetric cost, else 8-problem DMMA
  *           panels whose stragglers are finished by a warp-form tail kernel;
  *           problems the scaled form cannot represent are re-solved by the
- *           reference-form kernel).  Which problems migrate to the tail kernel
- *           depends on timing, so two calls agree to rounding (<= 1e-12
- *           relative), not bit for bit,
+ *           reference-form kernel, however many they are),
  *       1 = reference-form kernel only (per-problem Gibbs kernel, literal schedule),
- *       2 = warp-specialised variant of the DMMA-panel solver (kept for A/B measurements),
  *       3 = DMMA-panel solver (+ tail) for every K <= 64.
  * K > 64 (up to ~150) always takes the reference-form kernel.  The call is fully
  * asynchronous on `stream` (whether the cost is symmetric is decided on the
  * device: both variants of a solver are enqueued, one returns at once).
+ * precision: PILOT_F64 = the schedule above in double (within 1e-9 of POT);
+ * PILOT_F32 = log-domain Sinkhorn in float (within 1e-4; stop_thr is raised to
+ * what float can resolve), any K <= 64.
  */
 int pilot_sinkhorn_pairs(const double *props, int S, int K, const double *cost,
                          double reg, int num_iter_max, double stop_thr,
                          double tau, int check_every,
-                         const pilot_pair_range *range, int algo, double *out,
-                         int32_t *iters, int32_t *absorptions, int32_t *status,
+                         const pilot_pair_range *range, int algo, int precision,
+                         double *out, int32_t *iters, int32_t *absorptions,
+                         int32_t *status,
                          void *workspace, size_t workspace_bytes, void *stream);
 
 /*
  * (4) All-pairs exact EMD -- replaces the loop over ot.emd2(a_i, a_j, cost),
  * Trajectory.py:507-511 (b is rescaled to a's mass as emd2 does).
  * out[l] = optimal transport cost of local problem l; status/pivots may be NULL.
+ * precision: PILOT_F64 (costs, flows and potentials in double: within 1e-9 of
+ * POT) or PILOT_F32 (the same solver on float: within 1e-4).  1 <= K <= 64.
  */
 int pilot_emd_pairs(const double *props, int S, int K, const double *cost,
                     int64_t max_pivots, const pilot_pair_range *range,
-                    double *out, int32_t *status, int32_t *pivots,
-                    void *workspace, size_t workspace_bytes, void *stream);
+                    int precision, double *out, int32_t *status,
+                    int32_t *pivots, void *workspace, size_t workspace_bytes,
+                    void *stream);
 
 /*
  * (5) Packed per-rank results (as laid out by an all-gather: rank r's chunk at

@@ -11,7 +11,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "csrc", "libpilot_b200.so")
 
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 # constants mirrored from include/pilot_b200.h
 F32, F64 = 0, 1
@@ -21,11 +21,23 @@ METRICS = {"cosine": 0, "cos": 0, "euclidean": 1, "euclid": 1, "eu": 1, "e": 1, 
            "chebyshev": 4, "chebychev": 4, "chebyshev": 4, "cheby": 4, "cheb": 4, "ch": 4, "linf": 4,
            "correlation": 5, "co": 5}
 PAIRS_FULL, PAIRS_UPPER = 0, 1
+PRECISIONS = {"f64": F64, "fp64": F64, "float64": F64, "double": F64,
+              "f32": F32, "fp32": F32, "float32": F32, "single": F32}
+
+
+def precision_code(precision) -> int:
+    """'f64' (1e-9 parity tier, the default everywhere) or 'f32' (1e-4 tier) -> PILOT_F64 / PILOT_F32."""
+    if precision in (F32, F64) and not isinstance(precision, str):
+        return int(precision)
+    try:
+        return PRECISIONS[str(precision).lower()]
+    except KeyError:
+        raise ValueError(f"precision must be 'f64' or 'f32', got {precision!r}") from None
 ST_CONVERGED, ST_MAXITER, ST_NUMERIC, ST_UNBOUNDED = 0, 1, 2, 3
 WS_MEDIAN, WS_SINKHORN, WS_EMD = 0, 1, 2
 
 EXPORTS = (
-    "pilot_abi_version", "pilot_last_error", "pilot_range_count", "pilot_workspace_bytes",
+    "pilot_abi_version", "pilot_last_error", "pilot_range_count", "pilot_workspace_bytes", "pilot_launch_count",
     "pilot_hist", "pilot_props_finalize", "pilot_centroid_median", "pilot_cdist",
     "pilot_sinkhorn_pairs", "pilot_emd_pairs", "pilot_unpack_pairs", "pilot_pipe_peak",
 )
@@ -34,7 +46,8 @@ EXPORTS = (
 class PairRange(ctypes.Structure):
     """pilot_pair_range (include/pilot_b200.h)."""
     _fields_ = [("total", ctypes.c_int64), ("block", ctypes.c_int64), ("nranks", ctypes.c_int32),
-                ("rank", ctypes.c_int32), ("mode", ctypes.c_int32), ("reserved", ctypes.c_int32)]
+                ("rank", ctypes.c_int32), ("mode", ctypes.c_int32), ("reserved", ctypes.c_int32),
+                ("first", ctypes.c_int64)]
 
 
 class PilotLibraryError(RuntimeError):
@@ -64,6 +77,8 @@ def lib():
     L.pilot_range_count.argtypes = [prp]
     L.pilot_workspace_bytes.restype = sz
     L.pilot_workspace_bytes.argtypes = [i32, i64, i32, i32, i32]
+    L.pilot_launch_count.restype = ctypes.c_uint64
+    L.pilot_launch_count.argtypes = []
     L.pilot_hist.restype = i32
     L.pilot_hist.argtypes = [vp, vp, i64, i32, i32, vp, vp, vp, vp]
     L.pilot_props_finalize.restype = i32
@@ -73,10 +88,10 @@ def lib():
     L.pilot_cdist.restype = i32
     L.pilot_cdist.argtypes = [vp, i32, i32, i32, vp, vp, vp, vp]
     L.pilot_sinkhorn_pairs.restype = i32
-    L.pilot_sinkhorn_pairs.argtypes = [vp, i32, i32, vp, dbl, i32, dbl, dbl, i32, prp, i32, vp, vp, vp, vp,
+    L.pilot_sinkhorn_pairs.argtypes = [vp, i32, i32, vp, dbl, i32, dbl, dbl, i32, prp, i32, i32, vp, vp, vp, vp,
                                        vp, sz, vp]
     L.pilot_emd_pairs.restype = i32
-    L.pilot_emd_pairs.argtypes = [vp, i32, i32, vp, i64, prp, vp, vp, vp, vp, sz, vp]
+    L.pilot_emd_pairs.argtypes = [vp, i32, i32, vp, i64, prp, i32, vp, vp, vp, vp, sz, vp]
     L.pilot_unpack_pairs.restype = i32
     L.pilot_unpack_pairs.argtypes = [vp, i64, i32, prp, dbl, vp, vp]
     L.pilot_pipe_peak.restype = i32
@@ -91,6 +106,11 @@ def check(rc: int, what: str = "") -> None:
     if rc != 0:
         msg = lib().pilot_last_error().decode("utf-8", "replace")
         raise PilotLibraryError(f"{what or 'pilot_b200'} failed (rc={rc}): {msg}")
+
+
+def launch_count() -> int:
+    """Kernels launched by the library in this process so far."""
+    return int(lib().pilot_launch_count())
 
 
 def range_count(r: PairRange) -> int:

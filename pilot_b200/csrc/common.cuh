@@ -27,13 +27,19 @@ void set_error(const char *fmt, ...);
         }                                                                           \
     } while (0)
 
-#define PILOT_LAUNCH_CHECK() PILOT_CUDA(cudaGetLastError())
+// every kernel launch of the library is followed by this: it also feeds pilot_launch_count()
+#define PILOT_LAUNCH_CHECK()                \
+    do {                                    \
+        ::pilot::count_launch();            \
+        PILOT_CUDA(cudaGetLastError());     \
+    } while (0)
 
 int sm_count();
+void count_launch();
 
 // ---- pair-space mapping -----------------------------------
 struct PairMap {
-    long long total, block;
+    long long total, block, first;
     int nranks, rank, mode, S;
     long long n_local;
 };
@@ -73,8 +79,10 @@ __device__ __forceinline__ void upper_to_ij(long long g, int S, int &i, int &j)
     j = (int)(g - base + ii + 1);
 }
 
+// g counts from the start of the window [first, first + total)
 __device__ __forceinline__ void global_to_ij(const PairMap &pm, long long g, int &i, int &j)
 {
+    g += pm.first;
     if (pm.mode == PILOT_PAIRS_FULL) {
         i = (int)(g / pm.S);
         j = (int)(g - (long long)i * pm.S);

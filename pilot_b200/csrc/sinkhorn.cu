@@ -1,5 +1,6 @@
 // C-ABI entry of kernel (3): dispatch between the batched shared-Gibbs-kernel solver and
 // the reference-form kernel (reference call site: pilotpy/tools/Trajectory.py:513-515).
+#include <stdlib.h>
 #include "sinkhorn.cuh"
 
 namespace pilot {
@@ -28,7 +29,8 @@ size_t sinkhorn_ws_bytes(int K) { return sk_ws_bytes(K); }
 
 extern "C" int pilot_sinkhorn_pairs(const double *props, int S, int K, const double *cost, double reg,
                                     int num_iter_max, double stop_thr, double tau, int check_every,
-                                    const pilot_pair_range *range, int algo, double *out, int32_t *iters,
+                                    const pilot_pair_range *range, int algo, int precision, double *out,
+                                    int32_t *iters,
                                     int32_t *absorptions, int32_t *status, void *workspace,
                                     size_t workspace_bytes, void *stream)
 {
@@ -37,7 +39,8 @@ extern "C" int pilot_sinkhorn_pairs(const double *props, int S, int K, const dou
     PILOT_CHECK_ARG(S >= 1 && K >= 1, "pilot_sinkhorn_pairs: S=%d K=%d", S, K);
     PILOT_CHECK_ARG(reg > 0.0, "pilot_sinkhorn_pairs: reg must be > 0");
     PILOT_CHECK_ARG(num_iter_max >= 1 && check_every >= 1, "pilot_sinkhorn_pairs: bad iteration parameters");
-    PILOT_CHECK_ARG(algo >= 0 && algo <= 3, "pilot_sinkhorn_pairs: algo %d", algo);
+    PILOT_CHECK_ARG(algo == 0 || algo == 1 || algo == 3, "pilot_sinkhorn_pairs: algo %d", algo);
+    PILOT_CHECK_ARG(precision == PILOT_F64 || precision == PILOT_F32, "pilot_sinkhorn_pairs: precision=%d", precision);
     PILOT_CHECK_ARG(sinkhorn_ref_smem(K) <= 200 * 1024, "pilot_sinkhorn_pairs: K=%d too large (max ~150)", K);
     PILOT_CHECK_ARG(workspace_bytes >= sk_ws_bytes(K), "pilot_sinkhorn_pairs: workspace %zu < %zu bytes",
                     workspace_bytes, sk_ws_bytes(K));
@@ -47,6 +50,10 @@ extern "C" int pilot_sinkhorn_pairs(const double *props, int S, int K, const dou
     if (pm.n_local == 0) return 0;
     cudaStream_t st = (cudaStream_t)stream;
     SkParams prm{reg, stop_thr, tau, num_iter_max, check_every};
+    if (precision == PILOT_F32) {
+        set_error("pilot_sinkhorn_pairs: FP32 mode not built yet");
+        return -1;
+    }
     unsigned char *p = (unsigned char *)workspace;
     SkWs ws;
     ws.counter_fast = (unsigned long long *)p;
@@ -86,39 +93,31 @@ extern "C" int pilot_sinkhorn_pairs(const double *props, int S, int K, const dou
                         ws.n_redo, st);
         if (rc) return rc;
     }
-    if (algo != 2) {
-        const long long spw = skb_slots_per_warp();
-        long long ctas = (pm.n_local + spw - 1) / spw;
-        if (ctas > sm_count()) ctas = sm_count();
-        long long warp_cap = (pm.n_local + spw * ctas - 1) / (spw * ctas);
-        if (warp_cap > skb_warps()) warp_cap = skb_warps();
-        if (warp_cap < 1) warp_cap = 1;
-        for (int sym = warp_form ? 0 : 1; sym >= 0; --sym) {
-            rc = skb_launch(props, K, prm, pm, ws.setup, ws.scratch, (int)ctas, slot_cap, (int)warp_cap, sym != 0,
-                            tail, out, iters, absorptions, status, ws.counter_fast, ws.redo, ws.n_redo, st);
-            if (rc) return rc;
-        }
-        // the stragglers the panels handed over continue in warp form
-        for (int sym = warp_form ? 0 : 1; sym >= 0; --sym) {
-            rc = skt_launch(props, K, prm, pm, ws.setup, ws.scratch, sym != 0, tail, tail_counter, out, iters,
-                            absorptions, status, ws.redo, ws.n_redo, st);
-            if (rc) return rc;
-        }
-    } else {  // warp-specialised variant: same results, measured ~15 % slower, kept for A/B runs
-        const long long sps = skw_slots_per_set();
-        long long ctas = (pm.n_local + sps - 1) / sps;
-        if (ctas > sm_count()) ctas = sm_count();
-        long long set_cap = (pm.n_local + sps * ctas - 1) / (sps * ctas);
-        if (set_cap > skw_sets()) set_cap = skw_sets();
-        if (set_cap < 1) set_cap = 1;
-        for (int sym = 1; sym >= 0; --sym) {
-            rc = skw_launch(props, K, prm, pm, ws.setup, ws.scratch, (int)ctas, slot_cap, (int)set_cap, sym != 0, out,
-                            iters, absorptions, status, ws.counter_fast, ws.redo, ws.n_redo, st);
-            if (rc) return rc;
-        }
+    const long long spw = skb_slots_per_warp();
+    long long ctas = (pm.n_local + spw - 1) / spw;
+    if (ctas > sm_count()) ctas = sm_count();
+    long long warp_cap = (pm.n_local + spw * ctas - 1) / (spw * ctas);
+    if (warp_cap > skb_warps()) warp_cap = skb_warps();
+    if (warp_cap < 1) warp_cap = 1;
+    for (int sym = warp_form ? 0 : 1; sym >= 0; --sym) {
+        rc = skb_launch(props, K, prm, pm, ws.setup, ws.scratch, (int)ctas, slot_cap, (int)warp_cap, sym != 0,
+                        tail, out, iters, absorptions, status, ws.counter_fast, ws.redo, ws.n_redo, st);
+        if (rc) return rc;
+    }
+    // the stragglers the panels handed over continue in warp form
+    for (int sym = warp_form ? 0 : 1; sym >= 0; --sym) {
+        rc = skt_launch(props, K, prm, pm, ws.setup, ws.scratch, sym != 0, tail, tail_counter, out, iters,
+                        absorptions, status, ws.redo, ws.n_redo, st);
+        if (rc) return rc;
     }
     if (rc) return rc;
     // problems the scaled form could not represent (normally none): reference-form kernel
-    return sinkhorn_ref_launch(props, K, cost, prm, pm, ws.redo, ws.n_redo, SK_REDO_CAP, out, iters, absorptions,
+    // (PILOT_SK_REDO_CAP, tests only: a smaller list capacity, to exercise the overflow scan)
+    long long redo_cap = SK_REDO_CAP;
+    if (const char *e = getenv("PILOT_SK_REDO_CAP")) {
+        const long long v = atoll(e);
+        if (v >= 0 && v < redo_cap) redo_cap = v;
+    }
+    return sinkhorn_ref_launch(props, K, cost, prm, pm, ws.redo, ws.n_redo, redo_cap, out, iters, absorptions,
                                status, ws.counter_slow, st);
 }

@@ -1,4 +1,4 @@
-// Shared declarations of the Sinkhorn kernels (sinkhorn_ref.cu, sinkhorn_batched.cu, sinkhorn_ws.cu, sinkhorn_warp.cu).
+// Shared declarations of the Sinkhorn kernels (sinkhorn_ref.cu, sinkhorn_batched.cu, sinkhorn_tail.cu, sinkhorn_warp.cu).
 #pragma once
 #include "common.cuh"
 
@@ -10,6 +10,10 @@ struct SkParams {
 };
 
 constexpr long long SK_REDO_CAP = 1LL << 20;
+// out[] of a problem queued for the reference-form kernel: a NaN with this payload.  When more than
+// SK_REDO_CAP problems are queued the list overflows and the reference-form kernel finds the rest by
+// scanning out[] for the marker (sinkhorn_ref.cu, mode 2), so no problem is ever left unsolved.
+constexpr long long SK_REDO_MARK = 0x7ff8b200b200b200LL;
 
 // hand-over of straggler problems from the DMMA-panel kernel to the warp-form tail kernel
 struct SkTailRec {
@@ -48,15 +52,6 @@ int skt_launch(const double *props, int K, const SkParams &prm, const PairMap &p
                const double *scratch, bool symmetric, const SkTail &tail, unsigned long long *tail_counter,
                double *out, int *iters, int *absn, int *status, long long *redo, unsigned long long *n_redo,
                cudaStream_t st);
-
-// warp-specialised variant (sinkhorn_ws.cu)
-size_t skw_smem_bytes(int KP);
-size_t skw_scratch_bytes(int KP, int ctas);
-int skw_slots_per_set();
-int skw_sets();
-int skw_launch(const double *props, int K, const SkParams &prm, const PairMap &pm, double *setup, double *scratch,
-               int ctas, int slot_cap, int set_cap, bool symmetric, double *out, int *iters, int *absn, int *status,
-               unsigned long long *counter, long long *redo, unsigned long long *n_redo, cudaStream_t st);
 
 // one warp per problem, K0 in registers (sinkhorn_warp.cu): K <= swk_max_k(), symmetric cost
 int swk_max_k();

@@ -285,7 +285,7 @@ sinkhorn_batched_kernel(const double *__restrict__ props, int K, SkParams prm, P
                     } else {
                         const unsigned long long slot = atomicAdd(n_redo, 1ULL);
                         if ((long long)slot < SK_REDO_CAP) redo_list[slot] = sl[h];
-                        out[sl[h]] = __longlong_as_double(0x7ff8000000000000LL);
+                        out[sl[h]] = __longlong_as_double(SK_REDO_MARK);
                         if (status_out) status_out[sl[h]] = -1;
                     }
                 }

@@ -7,22 +7,28 @@
 //   err = || sum_i exp(-(M-alpha-beta)/reg + log u + log v) - b ||_2 ; stop on
 //   err <= stop_thr; NaN -> roll back to the previous (u, v); cap num_iter_max;
 //   result sum(M * Gamma).
-// One 64-thread CTA per problem (thread t owns row t and column t), persistent CTAs
-// pulling problems from a global counter.  This is the always-valid path: the batched
+// One CTA of roundup(K, 32) >= 64 threads per problem (thread t owns row t and column t),
+// persistent CTAs pulling problems from a global counter.  This is the always-valid path: the batched
 // shared-kernel solver (sinkhorn_batched.cu) hands it the problems it cannot represent.
 #include "sinkhorn.cuh"
 
 namespace pilot {
 
-constexpr int SKR_THREADS = 64;
+constexpr int SKR_MAX_WARPS = 8;   // K <= 256 by construction; the shared-memory check admits K <= ~150
+constexpr int SKR_SCAN = 256;      // problems per work item of the marker scan (mode 2)
 
+static int skr_threads(int K) { return K <= 64 ? 64 : ((K + 31) / 32) * 32; }
+
+// block reductions over the blockDim.x / 32 warps (2 for K <= 64), summed / maxed in warp order
 __device__ __forceinline__ double block_max64(double v, double *red)
 {
     v = warp_max_d(v);
     __syncthreads();
     if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
     __syncthreads();
-    return fmax(red[0], red[1]);
+    double r = red[0];
+    for (int w = 1; w < (int)(blockDim.x >> 5); ++w) r = fmax(r, red[w]);
+    return r;
 }
 __device__ __forceinline__ double block_sum64(double v, double *red)
 {
@@ -30,12 +36,17 @@ __device__ __forceinline__ double block_sum64(double v, double *red)
     __syncthreads();
     if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
     __syncthreads();
-    return red[0] + red[1];
+    double r = red[0];
+    for (int w = 1; w < (int)(blockDim.x >> 5); ++w) r += red[w];
+    return r;
 }
 
-__global__ void __launch_bounds__(SKR_THREADS)
+// mode 0: every local problem; mode 1: the problems of `list` (at most max_list of them); mode 2: only if
+// more than max_list problems were queued (the list overflowed): scan out[] for the redo marker the fast
+// kernels left behind and solve those (the listed ones were overwritten by mode 1 already).
+__global__ void __launch_bounds__(SKR_MAX_WARPS * 32)
 sinkhorn_ref_kernel(const double *__restrict__ props, int K, const double *__restrict__ M, SkParams prm,
-                    PairMap pm, const long long *__restrict__ list,
+                    PairMap pm, int mode, const long long *__restrict__ list,
                     const unsigned long long *__restrict__ n_list_dev, long long max_list,
                     double *__restrict__ out, int *__restrict__ iters_out, int *__restrict__ abs_out,
                     int *__restrict__ status_out, unsigned long long *__restrict__ counter)
@@ -46,28 +57,57 @@ sinkhorn_ref_kernel(const double *__restrict__ props, int K, const double *__res
     double *u = Km + (size_t)K * KS, *v = u + K, *up = v + K, *vp = up + K;
     double *al = vp + K, *be = al + K, *lu = be + K, *lv = lu + K, *red = lv + K;
     __shared__ long long s_l;
+    __shared__ int s_nfound;
+    __shared__ int s_found[SKR_SCAN];
     const int t = threadIdx.x;
+    const int NT = blockDim.x;
     const bool act = t < K;
     long long n_work = pm.n_local;
-    if (list) {
+    if (mode == 1) {
         n_work = (long long)*n_list_dev;
         if (n_work > max_list) n_work = max_list;
+    } else if (mode == 2) {
+        if ((long long)*n_list_dev <= max_list) return;
+        n_work = (pm.n_local + SKR_SCAN - 1) / SKR_SCAN;
     }
     const double reg = prm.reg;
+    int scan_pos = 0, scan_n = 0;
+    long long scan_base = 0;
 
     for (;;) {
-        __syncthreads();
-        if (t == 0) s_l = (long long)atomicAdd(counter, 1ULL);
-        __syncthreads();
-        long long w = s_l;
-        if (w >= n_work) break;
-        const long long l = list ? list[w] : w;
+        long long l;
+        if (mode == 2) {
+            // next marked problem of the current chunk, else fetch and scan the next chunk
+            while (scan_pos >= scan_n) {
+                __syncthreads();
+                if (t == 0) { s_l = (long long)atomicAdd(counter, 1ULL); s_nfound = 0; }
+                __syncthreads();
+                if (s_l >= n_work) return;
+                scan_base = s_l * SKR_SCAN;
+                for (int e = t; e < SKR_SCAN; e += NT) {
+                    const long long q = scan_base + e;
+                    if (q < pm.n_local && __double_as_longlong(out[q]) == SK_REDO_MARK)
+                        s_found[atomicAdd(&s_nfound, 1)] = e;
+                }
+                __syncthreads();
+                scan_n = s_nfound;
+                scan_pos = 0;
+            }
+            l = scan_base + s_found[scan_pos++];
+        } else {
+            __syncthreads();
+            if (t == 0) s_l = (long long)atomicAdd(counter, 1ULL);
+            __syncthreads();
+            const long long w = s_l;
+            if (w >= n_work) break;
+            l = mode == 1 ? list[w] : w;
+        }
         int si, sj;
         global_to_ij(pm, local_to_global(pm, l), si, sj);
         const double a = act ? props[(long long)si * K + t] : 0.0;
         const double b = act ? props[(long long)sj * K + t] : 0.0;
         if (act) { al[t] = 0.0; be[t] = 0.0; u[t] = 1.0 / K; v[t] = 1.0 / K; }
-        for (int e = t; e < K * K; e += SKR_THREADS) {
+        for (int e = t; e < K * K; e += NT) {
             const int i = e / K, j = e - i * K;
             Km[i * KS + j] = exp(-(__ldg(M + e)) / reg);
         }
@@ -106,7 +146,7 @@ sinkhorn_ref_kernel(const double *__restrict__ props, int K, const double *__res
                 }
                 anynan = false;  // u, v were just reset; the reference's NaN test sees the reset vectors
                 __syncthreads();
-                for (int e = t; e < K * K; e += SKR_THREADS) {
+                for (int e = t; e < K * K; e += NT) {
                     const int i = e / K, j = e - i * K;
                     Km[i * KS + j] = exp(-(__ldg(M + e) - al[i] - be[j]) / reg);
                 }
@@ -158,7 +198,7 @@ sinkhorn_ref_kernel(const double *__restrict__ props, int K, const double *__res
 size_t sinkhorn_ref_smem(int K)
 {
     const int KS = K | 1;
-    return sizeof(double) * ((size_t)K * KS + 8 * (size_t)K + 2);
+    return sizeof(double) * ((size_t)K * KS + 8 * (size_t)K + SKR_MAX_WARPS);
 }
 
 int sinkhorn_ref_launch(const double *props, int K, const double *cost, const SkParams &prm, const PairMap &pm,
@@ -170,16 +210,21 @@ int sinkhorn_ref_launch(const double *props, int K, const double *cost, const Sk
     const long long n_work = list ? (long long)sm_count() * 4 : pm.n_local;
     if (n_work <= 0) return 0;
     const size_t smem = sinkhorn_ref_smem(K);
+    const int threads = skr_threads(K);
+    PILOT_CHECK_ARG(threads <= SKR_MAX_WARPS * 32, "sinkhorn reference-form kernel: K=%d too large", K);
     PILOT_CUDA(cudaFuncSetAttribute(sinkhorn_ref_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = 1;
-    PILOT_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, sinkhorn_ref_kernel, SKR_THREADS, smem));
+    PILOT_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, sinkhorn_ref_kernel, threads, smem));
     if (per_sm < 1) per_sm = 1;
     long long ctas = (long long)sm_count() * per_sm;
     if (ctas > n_work) ctas = n_work;
-    PILOT_CUDA(cudaMemsetAsync(counter, 0, sizeof(unsigned long long), st));
-    sinkhorn_ref_kernel<<<(unsigned)ctas, SKR_THREADS, smem, st>>>(props, K, cost, prm, pm, list, n_list_dev, max_list,
-                                                                  out, iters, absorptions, status, counter);
-    PILOT_LAUNCH_CHECK();
+    // modes 1 and 2 run back to back on the stream and share the counter: reset it before each
+    for (int mode = list ? 1 : 0; mode <= (list ? 2 : 0); ++mode) {
+        PILOT_CUDA(cudaMemsetAsync(counter, 0, sizeof(unsigned long long), st));
+        sinkhorn_ref_kernel<<<(unsigned)ctas, threads, smem, st>>>(props, K, cost, prm, pm, mode, list, n_list_dev,
+                                                                  max_list, out, iters, absorptions, status, counter);
+        PILOT_LAUNCH_CHECK();
+    }
     return 0;
 }
 

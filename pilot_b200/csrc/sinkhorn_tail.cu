@@ -212,7 +212,7 @@ sinkhorn_tail_kernel(const double *__restrict__ props, int K, SkParams prm, Pair
         } else if (lane == 0) {
             const unsigned long long slot = atomicAdd(n_redo, 1ULL);
             if ((long long)slot < SK_REDO_CAP) redo_list[slot] = w;
-            out[w] = __longlong_as_double(0x7ff8000000000000LL);
+            out[w] = __longlong_as_double(SK_REDO_MARK);
             if (status_out) status_out[w] = -1;
         }
         __syncwarp();

@@ -140,7 +140,7 @@ def cdist(cent64: torch.Tensor, metric: str = "cosine") -> Tuple[torch.Tensor, t
 
 def sinkhorn_pairs(props: torch.Tensor, cost: torch.Tensor, reg: float, rng: PairRange, algo: int = 0,
                    num_iter_max: int = 1000, stop_thr: float = 1e-9, tau: float = 1e3, check_every: int = 20,
-                   want_info: bool = False, out: Optional[torch.Tensor] = None):
+                   want_info: bool = False, out: Optional[torch.Tensor] = None, precision="f64"):
     """Packed Sinkhorn costs of the problems `rng` assigns to rng.rank."""
     _require_cuda(props, cost)
     assert props.dtype == torch.float64 and cost.dtype == torch.float64
@@ -159,7 +159,8 @@ def sinkhorn_pairs(props: torch.Tensor, cost: torch.Tensor, reg: float, rng: Pai
     nbytes = lib().pilot_workspace_bytes(_lib.WS_SINKHORN, n, K, S, 0)
     ws = _workspace(nbytes, dev)
     check(lib().pilot_sinkhorn_pairs(_ptr(props), S, K, _ptr(cost), float(reg), int(num_iter_max), float(stop_thr),
-                                     float(tau), int(check_every), ctypes.byref(rng), int(algo), _ptr(out),
+                                     float(tau), int(check_every), ctypes.byref(rng), int(algo),
+                                     _lib.precision_code(precision), _ptr(out),
                                      _ptr(iters), _ptr(absn), _ptr(status), _ptr(ws), ws.numel(), _stream()),
           "pilot_sinkhorn_pairs")
     if want_info:
@@ -168,7 +169,7 @@ def sinkhorn_pairs(props: torch.Tensor, cost: torch.Tensor, reg: float, rng: Pai
 
 
 def emd_pairs(props: torch.Tensor, cost: torch.Tensor, rng: PairRange, max_pivots: int = 100000,
-              want_info: bool = False, out: Optional[torch.Tensor] = None):
+              want_info: bool = False, out: Optional[torch.Tensor] = None, precision="f64"):
     """Packed exact-EMD costs of the problems `rng` assigns to rng.rank."""
     _require_cuda(props, cost)
     assert props.dtype == torch.float64 and cost.dtype == torch.float64
@@ -183,9 +184,10 @@ def emd_pairs(props: torch.Tensor, cost: torch.Tensor, rng: PairRange, max_pivot
     if want_info:
         status = torch.zeros((max(n, 1),), dtype=torch.int32, device=dev)
         pivots = torch.zeros_like(status)
-    ws = _workspace(256, dev)
-    check(lib().pilot_emd_pairs(_ptr(props), S, K, _ptr(cost), int(max_pivots), ctypes.byref(rng), _ptr(out),
-                                _ptr(status), _ptr(pivots), _ptr(ws), ws.numel(), _stream()), "pilot_emd_pairs")
+    ws = _workspace(lib().pilot_workspace_bytes(_lib.WS_EMD, n, K, S, 0), dev)
+    check(lib().pilot_emd_pairs(_ptr(props), S, K, _ptr(cost), int(max_pivots), ctypes.byref(rng),
+                                _lib.precision_code(precision), _ptr(out), _ptr(status), _ptr(pivots), _ptr(ws),
+                                ws.numel(), _stream()), "pilot_emd_pairs")
     if want_info:
         return out[:n], status[:n], pivots[:n]
     return out[:n]

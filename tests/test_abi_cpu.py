@@ -33,9 +33,9 @@ def test_argument_validation_without_gpu():
     assert b"pilot_hist" in L.pilot_last_error()
     assert L.pilot_cdist(None, 4, 4, 0, None, None, None, None) < 0
     r = _lib.PairRange(total=10, block=0, nranks=1, rank=0, mode=0, reserved=0)
-    assert L.pilot_emd_pairs(1, 4, 3, 1, 0, ctypes.byref(r), 1, None, None, 1, 256, None) < 0
-    assert L.pilot_emd_pairs(1, 4, 65, 1, 0, ctypes.byref(r), 1, None, None, 1, 256, None) < 0
-    assert L.pilot_sinkhorn_pairs(1, 4, 3, 1, -1.0, 1000, 1e-9, 1e3, 20, ctypes.byref(r), 0, 1, None, None, None,
+    assert L.pilot_emd_pairs(1, 4, 3, 1, 0, ctypes.byref(r), 1, 1, None, None, 1, 256, None) < 0
+    assert L.pilot_emd_pairs(1, 4, 65, 1, 0, ctypes.byref(r), 1, 1, None, None, 1, 1 << 20, None) < 0
+    assert L.pilot_sinkhorn_pairs(1, 4, 3, 1, -1.0, 1000, 1e-9, 1e3, 20, ctypes.byref(r), 0, 1, 1, None, None, None,
                                   1, 1 << 30, None) < 0
     assert L.pilot_workspace_bytes(_lib.WS_SINKHORN, 0, 64, 0, 0) > (1 << 20)
     assert L.pilot_workspace_bytes(_lib.WS_MEDIAN, 0, 30, 0, 50) >= 30 * 50 * 2 * 256 * 4
