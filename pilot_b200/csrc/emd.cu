@@ -88,7 +88,8 @@ template <int NW, typename T> struct EmdWarp {
     static constexpr int KP = 32 * NW;  // padded types per side
     static constexpr int N = 2 * KP;    // nodes: rows 0..KP-1, columns KP..2KP-1
     static constexpr int NS = 2 * NW;   // slots per lane == mask words
-    unsigned sub[NS][N];                // subtree masks, word-major
+    static constexpr int SUBLD = N + 1; // odd word stride: the NS words of one node fall into different banks
+    unsigned sub[NS][SUBLD];            // subtree masks, word-major
     T flow[N];                          // flow on the arc (node, parent)
     T pi[N];                            // potentials; residual supplies/demands while the start basis is built
     unsigned short info[N];             // parent (low byte, 255 = none) | subtree size << 8
@@ -96,24 +97,9 @@ template <int NW, typename T> struct EmdWarp {
     unsigned char clist[N];             // compacted cycle nodes (bit 7: j-side)
 };
 
-template <int NW> __device__ __forceinline__ bool mask_bit(const unsigned (&m)[NW], int x)
-{
-    if (NW == 1) return (m[0] >> x) & 1u;
-    return ((x < 32 ? m[0] : m[NW - 1]) >> (x & 31)) & 1u;
-}
-template <int NW> __device__ __forceinline__ void mask_clear(unsigned (&m)[NW], int x)
-{
-#pragma unroll
-    for (int c = 0; c < NW; ++c)
-        if ((x >> 5) == c) m[c] &= ~(1u << (x & 31));
-}
-template <int NW> __device__ __forceinline__ int mask_lowest(const unsigned (&m)[NW])
-{
-#pragma unroll
-    for (int c = 0; c < NW; ++c)
-        if (m[c]) return c * 32 + __ffs(m[c]) - 1;
-    return -1;
-}
+// open-row / open-column sets of the start basis: one 64-bit mask each (warp-uniform)
+__device__ __forceinline__ unsigned bit64(unsigned long long m, unsigned x) { return (unsigned)(m >> x) & 1u; }
+__device__ __forceinline__ int lowest64(unsigned long long m) { return __ffsll((long long)m) - 1; }
 
 // ---- K(K-1) off-diagonal arcs in ascending cost order (ties and 2^-40-relative near-ties by index) ----
 __global__ void __launch_bounds__(1024) emd_sort_arcs_kernel(const double *__restrict__ cost, int K, int n_pad,
@@ -151,7 +137,7 @@ __global__ void __launch_bounds__(1024) emd_sort_arcs_kernel(const double *__res
         }
     const int n_arcs = K * (K - 1);
     for (int t = threadIdx.x; t < n_pad; t += blockDim.x) {
-        unsigned short e = 0xffffu;
+        unsigned short e = 0x3f3fu;  // (63, 63): row 63 and column 63 are never open together (a diagonal arc)
         if (t < n_arcs) {
             const int idx = (int)(key[t] & 0xfffULL);
             const int i = idx / K, j = idx - i * K;
@@ -314,14 +300,14 @@ emd_pairs_kernel(const double *__restrict__ props, int K, const double *__restri
         }
 
         // ---------------- start basis, parallel part: the diagonal arcs ----------------
-        unsigned ro[NW], co[NW];  // open surplus rows / open deficit columns (warp-uniform)
+        unsigned long long ro = 0ULL, co = 0ULL;  // open surplus rows / open deficit columns (warp-uniform)
 #pragma unroll
         for (int c = 0; c < NW; ++c) {
             const int idx = lane + 32 * c;
             const int r = idx, cn = KP + idx;
             const bool sur = valid[c] && av[c] >= bv[c];
-            ro[c] = __ballot_sync(FULLMASK, sur);
-            co[c] = __ballot_sync(FULLMASK, valid[c] && !sur);
+            ro |= (unsigned long long)__ballot_sync(FULLMASK, sur) << (32 * c);
+            co |= (unsigned long long)__ballot_sync(FULLMASK, valid[c] && !sur) << (32 * c);
 #pragma unroll
             for (int w = 0; w < NS; ++w) { sw->sub[w][r] = 0u; sw->sub[w][cn] = 0u; }
             unsigned short ir = 0x00ffu, ic = 0x00ffu;
@@ -349,22 +335,18 @@ emd_pairs_kernel(const double *__restrict__ props, int K, const double *__restri
 
         // ---------------- start basis, least-cost method on the residual (every lane runs it redundantly:
         // all stores are warp-uniform, so no lane ever reads another lane's value and no barrier is needed) ----
-        int nr = 0, nc = 0, n_ord = 0, root = 0;
-#pragma unroll
-        for (int c = 0; c < NW; ++c) { nr += __popc(ro[c]); nc += __popc(co[c]); }
+        int nr = __popcll(ro), nc = __popcll(co), n_ord = 0, root = 0;
         int st = PILOT_ST_CONVERGED;
         const bool greedy = nr > 0 && nc > 0;
         if (greedy) {
             for (int base = 0; nr + nc > 1 && base < n_arcs_pad; base += 32) {
                 const unsigned e = sArcs[base + lane];
-                unsigned hits = __ballot_sync(FULLMASK, e != 0xffffu && mask_bit<NW>(ro, (int)(e >> 8)) &&
-                                                            mask_bit<NW>(co, (int)(e & 0xffu)));
+                const unsigned er = e >> 8, ec = e & 0xffu;
+                unsigned hits = __ballot_sync(FULLMASK, (bit64(ro, er) & bit64(co, ec)) != 0u);
                 while (hits) {
                     const int src = __ffs(hits) - 1;
-                    hits &= hits - 1;
                     const unsigned ee = __shfl_sync(FULLMASK, e, src);
                     const int i = (int)(ee >> 8), j = (int)(ee & 0xffu);
-                    if (!(mask_bit<NW>(ro, i) && mask_bit<NW>(co, j))) continue;
                     const int xr = i, xc = KP + j;
                     const T ra = sw->pi[xr], rb = sw->pi[xc];
                     const bool close_row = nr == 1 ? false : (nc == 1 ? true : ra <= rb);
@@ -378,12 +360,14 @@ emd_pairs_kernel(const double *__restrict__ props, int K, const double *__restri
                     sw->flow[x] = f;
                     sw->sub[wlane][p] |= sw->sub[wlane][x];
                     sw->tmpc[n_ord++] = (unsigned char)x;
-                    if (close_row) { mask_clear<NW>(ro, i); --nr; } else { mask_clear<NW>(co, j); --nc; }
+                    // the arcs of this chunk that touch the node just closed are stale now
+                    if (close_row) { ro &= ~(1ULL << i); --nr; hits &= ~__ballot_sync(FULLMASK, er == (unsigned)i); }
+                    else           { co &= ~(1ULL << j); --nc; hits &= ~__ballot_sync(FULLMASK, ec == (unsigned)j); }
                     if (nr + nc <= 1) break;
                 }
             }
             if (nr + nc > 1) st = PILOT_ST_NUMERIC;  // cannot happen: every open (row, column) arc is in the list
-            root = nr ? mask_lowest<NW>(ro) : KP + mask_lowest<NW>(co);
+            root = nr ? lowest64(ro) : KP + lowest64(co);
             // potentials, root first (reverse closing order)
             sw->pi[root] = (T)0;
             for (int t = n_ord - 1; t >= 0; --t) {
@@ -396,11 +380,9 @@ emd_pairs_kernel(const double *__restrict__ props, int K, const double *__restri
             // a >= b everywhere (or a < b everywhere, only through rounding): every residual is ~0.  Chain the
             // (row, leaf column) pairs with zero-flow arcs row_t -> column_{t-1} (resp. the mirror image)
             const bool rows_open = nr > 0;
-            unsigned om[NW];
-#pragma unroll
-            for (int c = 0; c < NW; ++c) om[c] = rows_open ? ro[c] : co[c];
-            int prev = mask_lowest<NW>(om);
-            mask_clear<NW>(om, prev);
+            unsigned long long om = rows_open ? ro : co;
+            int prev = lowest64(om);
+            om &= om - 1;
             if (rows_open) {
                 root = prev;
                 sw->pi[prev] = (T)0;
@@ -411,9 +393,9 @@ emd_pairs_kernel(const double *__restrict__ props, int K, const double *__restri
                 sw->pi[prev] = -sM[prev * LDM + prev];
             }
             for (;;) {
-                const int cur = mask_lowest<NW>(om);
+                const int cur = lowest64(om);
                 if (cur < 0) break;
-                mask_clear<NW>(om, cur);
+                om &= om - 1;
                 if (rows_open) {
                     sw->info[cur] = (unsigned short)((sw->info[cur] & 0xff00u) | (unsigned)(KP + prev));
                     sw->flow[cur] = (T)0;
@@ -501,15 +483,24 @@ emd_pairs_kernel(const double *__restrict__ props, int K, const double *__restri
                 T best[NW];
 #pragma unroll
                 for (int c = 0; c < NW; ++c) { best[c] = (T)0; cand[c] = -1; }
-                int i = r0;
-                for (int rr = 0; rr < rows; ++rr) {
-                    const T pr = sw->pi[i];
+                // rows r0 .. r0+rows-1 (mod K) as at most two runs without a wrap test inside
+                int i = r0, left = rows;
+                while (left > 0) {
+                    const int run = min(left, K - i);
+                    const T *mrow = sM + i * LDM + lane;
+                    const T *prow = sw->pi + i;
+#pragma unroll 4
+                    for (int rr = 0; rr < run; ++rr) {
+                        const T pr = prow[rr];
 #pragma unroll
-                    for (int c = 0; c < NW; ++c) {
-                        const T rc = (sM[i * LDM + lane + 32 * c] + pr) - pj[c];
-                        if (rc < best[c]) { best[c] = rc; cand[c] = i; }
+                        for (int c = 0; c < NW; ++c) {
+                            const T rc = (mrow[rr * LDM + 32 * c] + pr) - pj[c];
+                            if (rc < best[c]) { best[c] = rc; cand[c] = i + rr; }
+                        }
                     }
-                    if (++i == K) i = 0;
+                    left -= run;
+                    i += run;
+                    if (i == K) i = 0;
                 }
                 r0 = i;
                 since += rows;
@@ -668,7 +659,7 @@ static int emd_launch(const double *props, int K, const double *cost, const Pair
         if (fast_limit > 32) fast_limit = 32;
     }
     // rows per major pricing pass (PILOT_EMD_SCAN_ROWS overrides, measurements only)
-    int scan_rows = K <= 16 ? K : 16;
+    int scan_rows = K <= 16 ? K : (K <= 32 ? 16 : 32);  // measured at K = 64: 4/8/16/32/64 rows -> 25.6/29.1/31.7/33.3/32.3 M pairs/s
     if (const char *e = getenv("PILOT_EMD_SCAN_ROWS")) {
         scan_rows = atoi(e);
         if (scan_rows < 1) scan_rows = 1;
