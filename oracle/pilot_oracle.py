@@ -20,6 +20,10 @@ Pinning status
   setup.py:19), absent from /root/reference and not installable here ->
   **parity unpinned** against POT; anchored on SciPy-HiGHS (EMD optimum),
   closed-form known answers, and Sinkhorn marginal invariants.
+  The pin closes by itself wherever POT exists: ``pot()`` returns the real
+  module when ``import ot`` works (site-packages or baseline/_ref), and then
+  tests/test_oracle_vs_pot.py checks this restatement against it and
+  bench.py's reference arm times POT itself (``kind: "pot <version>"``).
 """
 from __future__ import annotations
 
@@ -35,6 +39,34 @@ import scipy.spatial.distance as ssd
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB_PATH = os.path.join(_HERE, "libpilot_oracle.so")
 _lib = None
+_pot = False  # not probed yet
+
+
+def pot():
+    """The real POT module (``ot``) if it can be imported -- from site-packages or from an offline
+    install under baseline/_ref -- else None.  Never required; when present it pins the restatement."""
+    global _pot
+    if _pot is False:
+        import importlib
+        import sys
+        ref = os.path.join(os.path.dirname(_HERE), "baseline", "_ref")
+        added = False
+        if os.path.isdir(ref) and ref not in sys.path:
+            sys.path.append(ref)
+            added = True
+        try:
+            mod = importlib.import_module("ot")
+            _pot = mod if hasattr(mod, "emd2") and hasattr(mod, "sinkhorn2") else None
+        except Exception:
+            _pot = None
+        if _pot is None and added:
+            sys.path.remove(ref)
+    return _pot
+
+
+def pot_version():
+    m = pot()
+    return None if m is None else str(getattr(m, "__version__", "unknown"))
 
 
 class _EmdStats(ctypes.Structure):

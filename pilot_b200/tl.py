@@ -202,6 +202,7 @@ def _embedding_to_device(data) -> torch.Tensor:
     side.wait_stream(main)
     with torch.cuda.stream(side):
         X_dev.copy_(host, non_blocking=True)
+    X_dev.record_stream(side)  # the allocator must not hand the block out again while the copy is in flight
     done = torch.cuda.Event()
     done.record(side)
     X_dev._pilot_ready = done  # consumed by _cost_device
@@ -239,11 +240,12 @@ def _cost_frame(dis: np.ndarray, cells) -> pd.DataFrame:
     return _labelled_square(dis.T, cells, "cell_types")
 
 
-def _emd_frame(EMD: np.ndarray, samples_id: List) -> pd.DataFrame:
-    # DataFrame.from_dict(EMD).T (Trajectory.py:518) is the transpose
+def _emd_frame(EMD: np.ndarray, samples_id: List, EMD_T: Optional[np.ndarray] = None) -> pd.DataFrame:
+    # DataFrame.from_dict(EMD).T (Trajectory.py:518) is the transpose; EMD_T, when given, is an independent
+    # C-contiguous copy of it that the frame takes over without another pass over S x S doubles
     if len(samples_id) == 0 or np.asarray(samples_id).dtype.kind in "iu":
         return _labelled_square_reference(EMD, samples_id, "sampleID")
-    return _labelled_square(EMD.T, samples_id, "sampleID")
+    return _labelled_square(EMD.T if EMD_T is None else EMD_T, samples_id, "sampleID")
 
 
 # ---------------------------------------------------------------------------
@@ -277,11 +279,11 @@ def Cluster_Representations(df, cell_col=0, sample_col=1, regulizer=0.2, normali
 # Stage 2: cost matrix (Trajectory.py:441-475)
 # ---------------------------------------------------------------------------
 def _cost_device(lab: _Labels, X_dev: torch.Tensor, metric) -> Tuple[torch.Tensor, torch.Tensor]:
-    if X_dev.shape[0] != lab.n:
-        raise ValueError(f"Item wrong length {lab.n} instead of {X_dev.shape[0]}.")
     ready = getattr(X_dev, "_pilot_ready", None)
     if ready is not None:
         torch.cuda.current_stream(X_dev.device).wait_event(ready)
+    if X_dev.shape[0] != lab.n:
+        raise ValueError(f"Item wrong length {lab.n} instead of {X_dev.shape[0]}.")
     _, cent64_raw = ops.centroid_median(X_dev, lab.ct_dev, lab.K_raw)
     cent64 = cent64_raw.index_select(0, lab.perm_k_dev.long()).contiguous()
     cost, cost_norm, _ = ops.cdist(cent64, metric)
@@ -323,10 +325,13 @@ def wasserstein_d(Clu_rep, cost, regularized="unreg", reg=0.1):
     if len(samples_id) == 0:
         EMD = np.zeros((0, 0))
         return EMD, _emd_frame(EMD, samples_id)
+    sym = None
     if regularized == "unreg":
         _check_emd_inputs(P, C)
-    EMD = pairs.all_pairs(_to_device(P), _to_device(C), regularized, reg).cpu().numpy()
-    return EMD, _emd_frame(EMD, samples_id)
+        sym = pairs.cost_is_symmetric_metric_like(C)  # K x K on the host: no device round trip
+    EMD, EMD_T = pairs.all_pairs_host(_to_device(P), _to_device(C), regularized, reg, symmetric=sym,
+                                      with_transpose=True)
+    return EMD, _emd_frame(EMD, samples_id, EMD_T)
 
 
 # ---------------------------------------------------------------------------
@@ -348,6 +353,8 @@ def wasserstein_distance(adata, emb_matrix="X_PCA", clusters_col="cell_types", s
                          return_sil_ari=False):
     """Drop-in for ``pilotpy.tl.wasserstein_distance``: writes ``data``, ``annot``,
     ``proportions``, ``cost``, ``EMD_df``, ``EMD`` and ``real_labels`` into ``adata.uns``."""
+    if return_sil_ari:
+        _require_clustering_tail()  # fail before any device work or side effect, not after (ADVICE r1)
     X_dev = None
     if data_type == "scRNA":
         # stage the embedding straight from the caller's array (no detour through the DataFrame) and
@@ -368,24 +375,70 @@ def wasserstein_distance(adata, emb_matrix="X_PCA", clusters_col="cell_types", s
     cost, cost_norm = _cost_device(lab, X_dev, metric)
     # enqueue the pair stage before the first device-to-host read, so that the host-side checks and the
     # construction of the result containers overlap it (its result is dropped if a check raises)
-    emd_dev = pairs.all_pairs(props, cost_norm, regularized, reg)
-    props_h = props.cpu().numpy()
-    if int(counts.sum().item()) != lab.n:
-        raise ValueError("label codes out of range")
-    if regularized == "unreg":
-        _check_emd_inputs(props_h, np.empty((lab.K, lab.K)))
+    if lab.S * lab.S * 8 >= (1 << 28):
+        # big matrix: band pipeline, the rows cross PCIe while later bands are solved (pairs.all_pairs_host)
+        props_h = props.cpu().numpy()
+        if int(counts.sum().item()) != lab.n:
+            raise ValueError("label codes out of range")
+        if regularized == "unreg":
+            _check_emd_inputs(props_h, np.empty((lab.K, lab.K)))
+        EMD, EMD_T = pairs.all_pairs_host(props, cost_norm, regularized, reg, with_transpose=True)
+    else:
+        emd_dev = pairs.all_pairs(props, cost_norm, regularized, reg)
+        props_h = props.cpu().numpy()
+        if int(counts.sum().item()) != lab.n:
+            raise ValueError("label codes out of range")
+        if regularized == "unreg":
+            _check_emd_inputs(props_h, np.empty((lab.K, lab.K)))
+        EMD, EMD_T = emd_dev.cpu().numpy(), None
 
     adata.uns["proportions"] = _props_dict(lab.samples, props_h)
     dis = cost.cpu().numpy()
     adata.uns["cost"] = _cost_frame(dis, lab.cells)
-    EMD = emd_dev.cpu().numpy()
-    adata.uns["EMD_df"] = _emd_frame(EMD, list(adata.uns["proportions"].keys()))
+    adata.uns["EMD_df"] = _emd_frame(EMD, list(adata.uns["proportions"].keys()), EMD_T)
     adata.uns["EMD"] = EMD
 
     if return_sil_ari:
+        # the reference's Leiden / ARI / silhouette tail (Trajectory.py:107-113) is a consumer of the matrix
+        # (scanpy + leidenalg + sklearn): run the reference's own functions on it
+        Clustering, Sil_computing = _require_clustering_tail()
+        predicted_labels, ARI, real_labels = Clustering(EMD / EMD.max(), annot, metric=metric, res=res, steper=steper)
+        adata.uns["real_labels"] = real_labels
+        adata.uns["Sil"] = Sil_computing(EMD / EMD.max(), real_labels, metric=metric)
+        adata.uns["ARI"] = ARI
+    else:
+        # first status per sample, via the first-appearance cell index the histogram kernel produced
+        adata.uns["real_labels"] = list(annot["status"].iloc[lab.first_smp])
+
+
+def _require_clustering_tail():
+    """(Clustering, Sil_computing) of the reference (Trajectory.py:527-612).  They need scanpy, leidenalg and
+    scikit-learn and consume the finished matrix; this package does not re-implement graph clustering."""
+    try:
+        from pilotpy.tools.Trajectory import Clustering, Sil_computing  # type: ignore
+    except Exception as exc:
         raise NotImplementedError(
-            "return_sil_ari=True runs the reference's Leiden/ARI/silhouette tail (Trajectory.py:107-113, "
-            "scanpy + leidenalg), which is outside the patient-distance hot path (SURVEY.md 8f #4); call "
-            "pilotpy.tl.Clustering / Sil_computing on adata.uns['EMD'] instead.")
-    # first status per sample, via the first-appearance cell index the histogram kernel produced
-    adata.uns["real_labels"] = list(annot["status"].iloc[lab.first_smp])
+            "return_sil_ari=True runs the reference's Leiden/ARI/silhouette tail (Trajectory.py:107-113), which "
+            "needs pilotpy with scanpy + leidenalg importable; it is a consumer of the distance matrix, outside "
+            f"the patient-distance hot path (SURVEY.md 8f #2, #4).  Import failed with: {exc!r}") from exc
+    return Clustering, Sil_computing
+
+
+def Precomputed_distance(adata, distances, cost_df, features_matrix, emb_matrix="X_PCA", clusters_col="cell_types",
+                         sample_col="sampleID", status="status", data_type="scRNA"):
+    """Store externally computed sample distances in ``adata.uns`` (Trajectory.py:1687-1727): the reference's
+    bring-your-own-backend seam.  The reference body reads an undefined ``data_type`` (:1716, a NameError in
+    2.0.6); here it is a keyword argument with the value the other entry points default to."""
+    if data_type == "scRNA":
+        data, annot = extract_data_anno_scRNA_from_h5ad(adata, emb_matrix=emb_matrix, clusters_col=clusters_col,
+                                                        sample_col=sample_col, status=status)
+    else:
+        data, annot = extract_data_anno_pathomics_from_h5ad(adata, var_names=list(adata.var_names),
+                                                            clusters_col=clusters_col, sample_col=sample_col,
+                                                            status=status)
+    adata.uns["data"] = data
+    adata.uns["annot"] = annot
+    adata.uns["proportions"] = features_matrix
+    adata.uns["cost"] = cost_df
+    adata.uns["EMD"] = distances
+    adata.uns["real_labels"] = return_real_labels(annot)

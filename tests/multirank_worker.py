@@ -1,0 +1,58 @@
+"""Worker of tests/test_gpu_multirank.py (launched under torchrun, one rank per GPU, NCCL): the matrices
+assembled from the ranks' shares with the NCCL all-gather must equal a single-rank solve of the same
+problems entry by entry -- exact EMD bit-identical, Sinkhorn <= 1e-12 relative -- for the device path
+(pairs.all_pairs), the banded host path (pairs.all_pairs_host) and the public tl.wasserstein_d."""
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from oracle import pilot_oracle as po  # noqa: E402  (checker)
+from pilot_b200 import pairs, synth, tl  # noqa: E402
+
+
+def main():
+    rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+    torch.cuda.set_device(int(os.environ["LOCAL_RANK"]))
+    dist.init_process_group("nccl", device_id=torch.device("cuda", int(os.environ["LOCAL_RANK"])))
+    worst = 0.0
+    for S, K, reg in ((301, 30, 0.1), (257, 64, 0.1), (120, 40, 0.02), (97, 10, 0.1)):
+        P, M = synth.make_pairs(S, K, seed=60 + K)
+        Pd, Md = torch.from_numpy(P).cuda(), torch.from_numpy(M).cuda()
+        for regularized in ("unreg", "reg"):
+            multi = pairs.all_pairs(Pd, Md, regularized, reg)
+            single = pairs.all_pairs(Pd, Md, regularized, reg, single_rank=True)
+            host, host_T = pairs.all_pairs_host(Pd, Md, regularized, reg, n_bands=5, with_transpose=True)
+            if regularized == "unreg":
+                assert torch.equal(multi, single), f"EMD differs between {world} ranks and 1 rank (S={S}, K={K})"
+                assert np.array_equal(host, single.cpu().numpy())
+            else:
+                rel = float(((multi - single).abs() / single.abs()).max().item())
+                worst = max(worst, rel)
+                assert rel <= 1e-12, f"Sinkhorn differs by {rel} between {world} ranks and 1 rank"
+                np.testing.assert_allclose(host, single.cpu().numpy(), rtol=1e-12)
+            assert np.array_equal(host_T, host.T)
+            # every rank holds the same matrix
+            ref = multi.clone()
+            dist.broadcast(ref, 0)
+            assert torch.equal(ref, multi), "ranks disagree after the all-gather"
+        rep = {f"s{i}": P[i] for i in range(S)}
+        EMD, df = tl.wasserstein_d(rep, M)
+        if rank == 0:
+            r = np.random.default_rng(S)
+            for i, j in zip(r.integers(0, S, 40), r.integers(0, S, 40)):
+                w = po.emd2(P[i], P[j], M)
+                assert abs(EMD[i, j] - w) <= 1e-9 * max(w, 1e-300) + 1e-15
+            assert np.array_equal(df.to_numpy(), EMD.T)
+    dist.barrier()
+    if rank == 0:
+        print(f"MULTIRANK OK world={world} sinkhorn_worst_rel={worst:.3e}", flush=True)
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -227,3 +227,67 @@ def test_properties_at_scale():
         assert abs(tri[i, j] - po.emd2(P[i], P[j], M)) <= EMD_RTOL * max(tri[i, j], 1e-12)
         w = po.sinkhorn2(P[i], P[j], M, 0.1)
         assert abs(sk1[i, j] - w) <= SK_RTOL * w
+
+
+@pytest.mark.parametrize("mode", [_lib.PAIRS_FULL, _lib.PAIRS_UPPER])
+def test_pair_range_windows(mode):
+    """A window [first, first + total) of the pair space solves exactly the problems of that window."""
+    S, K = 37, 12
+    P, M = synth.make_pairs(S, K, seed=21)
+    Pd, Md = dev(P), dev(M)
+    total = ops.n_pairs(S, mode)
+    full = ops.emd_pairs(Pd, Md, ops.make_range(total, mode)).cpu().numpy()
+    for first, cnt, nranks in [(0, 5, 1), (17, 101, 1), (total - 9, 9, 1), (40, 300, 3)]:
+        got = np.full(cnt, np.nan)
+        for rank in range(nranks):
+            block = 7 if nranks > 1 else cnt
+            rng = _lib.PairRange(total=cnt, block=block, nranks=nranks, rank=rank, mode=mode, reserved=0, first=first)
+            out = ops.emd_pairs(Pd, Md, rng).cpu().numpy()
+            for l in range(len(out)):
+                got[pairs.local_to_global(l, block, nranks, rank)] = out[l]
+        assert np.array_equal(got, full[first:first + cnt])
+        sk = ops.sinkhorn_pairs(Pd, Md, 0.1, _lib.PairRange(total=cnt, block=cnt, nranks=1, rank=0, mode=mode,
+                                                            reserved=0, first=first)).cpu().numpy()
+        for l in (0, cnt - 1):
+            i, j = pairs.global_to_ij(first + l, S, mode)
+            assert abs(sk[l] - po.sinkhorn2(P[i], P[j], M, 0.1)) <= SK_RTOL * sk[l]
+
+
+@pytest.mark.parametrize("regularized", ["unreg", "reg"])
+@pytest.mark.parametrize("n_bands", [1, 3, 7, 64])
+def test_all_pairs_host_bands(regularized, n_bands):
+    """The banded host pipeline returns the same matrix as the one-window device path, and its transpose."""
+    S, K = 61, 9
+    P, M = synth.make_pairs(S, K, seed=13)
+    want = pairs.all_pairs(dev(P), dev(M), regularized, 0.1).cpu().numpy()
+    got, got_T = pairs.all_pairs_host(dev(P), dev(M), regularized, 0.1, n_bands=n_bands, with_transpose=True)
+    if regularized == "unreg":
+        assert np.array_equal(got, want)
+    else:
+        np.testing.assert_allclose(got, want, rtol=1e-12)
+    assert np.array_equal(got_T, got.T) and got_T.flags.c_contiguous and got.flags.c_contiguous
+    asym = np.random.default_rng(5).random((K, K))
+    got2, got2_T = pairs.all_pairs_host(dev(P), dev(asym), regularized, 0.1, n_bands=n_bands, with_transpose=True)
+    assert np.array_equal(got2_T, got2.T)
+    np.testing.assert_allclose(got2, pairs.all_pairs(dev(P), dev(asym), regularized, 0.1).cpu().numpy(), rtol=1e-12)
+
+
+def test_wasserstein_d_big_matrix_band_pipeline():
+    """S large enough for the band pipeline to kick in by itself (S*S*8 >= 256 MB): both containers, exact."""
+    from pilot_b200 import tl
+    S, K = 6000, 8
+    P, M = synth.make_pairs(S, K, seed=17)
+    rep = {f"s{i:05d}": P[i] for i in range(S)}
+    EMD, df = tl.wasserstein_d(rep, M)
+    assert EMD.shape == (S, S) and np.array_equal(EMD, EMD.T) and np.abs(np.diag(EMD)).max() == 0.0
+    assert df.index.name == "sampleID" and list(df.columns[:3]) == ["s00000", "s00001", "s00002"]
+    assert np.array_equal(df.to_numpy(), EMD.T)
+    r = np.random.default_rng(2)
+    for i, j in zip(r.integers(0, S, 300), r.integers(0, S, 300)):
+        w = po.emd2(P[i], P[j], M)
+        assert abs(EMD[i, j] - w) <= EMD_RTOL * max(w, 1e-300) + 1e-15
+    SK, sdf = tl.wasserstein_d(rep, M, regularized="reg", reg=0.1)
+    assert np.array_equal(sdf.to_numpy(), SK.T)
+    for i, j in zip(r.integers(0, S, 100), r.integers(0, S, 100)):
+        w = po.sinkhorn2(P[i], P[j], M, 0.1)
+        assert abs(SK[i, j] - w) <= SK_RTOL * w

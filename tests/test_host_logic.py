@@ -105,3 +105,40 @@ def test_labelled_frames_equal_the_reference_statements(kind):
         assert type(got.index) is type(want.index) and type(got.columns) is type(want.columns)
         assert got.index.name == want.index.name and got.columns.name == want.columns.name
         np.testing.assert_array_equal(got.to_numpy(), mat.T)
+
+
+def test_band_rows_cover_the_pair_space():
+    from pilot_b200 import _lib, pairs
+    for S in (1, 2, 3, 17, 100, 20000):
+        for mode in (_lib.PAIRS_FULL, _lib.PAIRS_UPPER):
+            total = S * S if mode == _lib.PAIRS_FULL else S * (S - 1) // 2
+            assert pairs.row_start(S, S, mode) == total
+            for nb in (1, 2, 7, 64, 1000):
+                e = pairs.band_rows(S, mode, nb)
+                assert e[0] == 0 and e[-1] == S and all(a < b for a, b in zip(e[:-1], e[1:]))
+                sizes = [pairs.row_start(b, S, mode) - pairs.row_start(a, S, mode) for a, b in zip(e[:-1], e[1:])]
+                assert sum(sizes) == total
+                if S == 20000 and nb == 64:
+                    assert max(sizes) <= 1.2 * total / nb  # balanced
+    # a row's first problem maps back to (row, first column)
+    for S in (5, 33):
+        for i in range(S - 1):
+            assert pairs.global_to_ij(pairs.row_start(i, S, _lib.PAIRS_UPPER), S, _lib.PAIRS_UPPER) == (i, i + 1)
+            assert pairs.global_to_ij(pairs.row_start(i, S, _lib.PAIRS_FULL), S, _lib.PAIRS_FULL) == (i, 0)
+
+
+def test_precomputed_distance_writes_the_uns_contract(tmp_path, monkeypatch):
+    """Precomputed_distance (Trajectory.py:1687-1727) is host-only; data_type is a keyword here (the reference
+    reads an undefined name, :1716)."""
+    import pandas as pd
+    from pilot_b200 import synth, tl
+    monkeypatch.chdir(tmp_path)
+    X, obs = synth.make_cells(500, 4, 3, 5, seed=1)
+    adata = synth.FakeAnnData(obs, obsm={"X_PCA": X})
+    D = np.arange(25.0).reshape(5, 5)
+    cost = pd.DataFrame(np.eye(3))
+    feats = {"a": np.ones(3)}
+    tl.Precomputed_distance(adata, D, cost, feats)
+    assert adata.uns["EMD"] is D and adata.uns["cost"] is cost and adata.uns["proportions"] is feats
+    assert list(adata.uns["annot"].columns) == ["cell_type", "sampleID", "status"]
+    assert len(adata.uns["real_labels"]) == 5 and len(adata.uns["data"]) == 500
