@@ -50,10 +50,7 @@ extern "C" int pilot_sinkhorn_pairs(const double *props, int S, int K, const dou
     if (pm.n_local == 0) return 0;
     cudaStream_t st = (cudaStream_t)stream;
     SkParams prm{reg, stop_thr, tau, num_iter_max, check_every};
-    if (precision == PILOT_F32) {
-        set_error("pilot_sinkhorn_pairs: FP32 mode not built yet");
-        return -1;
-    }
+
     unsigned char *p = (unsigned char *)workspace;
     SkWs ws;
     ws.counter_fast = (unsigned long long *)p;
@@ -64,9 +61,24 @@ extern "C" int pilot_sinkhorn_pairs(const double *props, int S, int K, const dou
         return sinkhorn_ref_launch(props, K, cost, prm, pm, nullptr, nullptr, 0, out, iters, absorptions, status,
                                    ws.counter_slow, st);
     const int KP = skb_pad(K);
+    ws.redo = (long long *)(p + 256 + skb_setup_bytes(KP) + skb_scratch_bytes(KP, sm_count()));
+    long long redo_cap = SK_REDO_CAP;
+    // (PILOT_SK_REDO_CAP, tests only: a smaller list capacity, to exercise the overflow scan)
+    if (const char *e = getenv("PILOT_SK_REDO_CAP")) {
+        const long long v = atoll(e);
+        if (v >= 0 && v < redo_cap) redo_cap = v;
+    }
+    if (precision == PILOT_F32) {
+        // single precision: per-problem kernel in registers (sinkhorn_f32.cu); what it cannot carry (NaN/Inf,
+        // zero masses) goes to the FP64 reference-form kernel like in the FP64 mode
+        rc = skf_launch(props, K, cost, prm, pm, out, iters, absorptions, status, ws.counter_fast, ws.redo,
+                        ws.n_redo, st);
+        if (rc) return rc;
+        return sinkhorn_ref_launch(props, K, cost, prm, pm, ws.redo, ws.n_redo, redo_cap, out, iters, absorptions,
+                                   status, ws.counter_slow, st);
+    }
     ws.setup = (double *)(p + 256);
     ws.scratch = (double *)(p + 256 + skb_setup_bytes(KP));
-    ws.redo = (long long *)(p + 256 + skb_setup_bytes(KP) + skb_scratch_bytes(KP, sm_count()));
     unsigned char *ptail = (unsigned char *)ws.redo + (size_t)SK_REDO_CAP * sizeof(long long);
     SkTail tail;
     tail.rec = (SkTailRec *)ptail;
@@ -112,12 +124,6 @@ extern "C" int pilot_sinkhorn_pairs(const double *props, int S, int K, const dou
     }
     if (rc) return rc;
     // problems the scaled form could not represent (normally none): reference-form kernel
-    // (PILOT_SK_REDO_CAP, tests only: a smaller list capacity, to exercise the overflow scan)
-    long long redo_cap = SK_REDO_CAP;
-    if (const char *e = getenv("PILOT_SK_REDO_CAP")) {
-        const long long v = atoll(e);
-        if (v >= 0 && v < redo_cap) redo_cap = v;
-    }
     return sinkhorn_ref_launch(props, K, cost, prm, pm, ws.redo, ws.n_redo, redo_cap, out, iters, absorptions,
                                status, ws.counter_slow, st);
 }

@@ -59,4 +59,9 @@ int swk_launch(const double *props, int K, const SkParams &prm, const PairMap &p
                int *iters, int *absn, int *status, unsigned long long *counter, long long *redo,
                unsigned long long *n_redo, cudaStream_t st);
 
+// FP32 mode: one warp per problem, per-problem kernel in registers (sinkhorn_f32.cu), K <= 64
+int skf_launch(const double *props, int K, const double *cost, const SkParams &prm, const PairMap &pm, double *out,
+               int *iters, int *absn, int *status, unsigned long long *counter, long long *redo,
+               unsigned long long *n_redo, cudaStream_t st);
+
 }  // namespace pilot

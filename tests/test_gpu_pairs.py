@@ -150,6 +150,44 @@ def test_sinkhorn_redo_list_overflow(K, cap, monkeypatch):
     np.testing.assert_allclose(got.reshape(S, S)[:3], want, rtol=SK_RTOL, equal_nan=True)
 
 
+@pytest.mark.parametrize("K,reg,S", [(10, 0.1, 20), (30, 0.1, 100), (64, 0.1, 40), (64, 0.01, 16), (40, 0.02, 16),
+                                     (5, 0.5, 12), (30, 0.01, 16), (33, 0.05, 16), (64, 0.05, 24), (1, 0.1, 3)])
+def test_sinkhorn_fp32_mode(K, reg, S):
+    """north_star's FP32 tier: single-precision Sinkhorn (per-problem kernel in registers) within 1e-4 relative
+    of the FP64 oracle, at the C2 (K=30, reg 0.1), C4 (K=64, reg 0.01) and C5 (K=64, reg 0.1) shapes and others.
+    The iteration count may differ from the FP64 schedule only through the float stop threshold (5e-7)."""
+    P, M = synth.make_pairs(S, K, seed=400 + K)
+    if K == 1:
+        M = np.zeros((1, 1))
+    rng = ops.make_range(S * S, _lib.PAIRS_FULL)
+    out, iters, absn, status = ops.sinkhorn_pairs(dev(P), dev(M), reg, rng, want_info=True, precision="f32")
+    want, witers, wabs = po.sinkhorn_rows(P, M, reg, 0, S)
+    got = out.cpu().numpy().reshape(S, S)
+    np.testing.assert_allclose(got, want, rtol=1e-4, atol=1e-7)
+    it = iters.cpu().numpy().reshape(S, S)
+    assert (it <= witers).all() and (it >= 1).all()
+    assert (it % 20 == 1).all() or (it == 1000).any() or K == 1
+    st = status.cpu().numpy()
+    assert ((st == 0) | (st == 1)).all()
+
+
+def test_sinkhorn_fp32_zero_mass_and_asymmetric_cost():
+    K, S = 12, 6
+    P, M = synth.make_pairs(S, K, seed=3)
+    P[1, 3] = 0.0
+    P[1] /= P[1].sum()
+    rng = ops.make_range(S * S, _lib.PAIRS_FULL)
+    a = ops.sinkhorn_pairs(dev(P), dev(M), 0.01, rng, precision="f32").cpu().numpy()
+    want, _, _ = po.sinkhorn_rows(P, M, 0.01, 0, S)
+    np.testing.assert_allclose(a, want.ravel(), rtol=1e-4, equal_nan=True)
+    Ma = np.random.default_rng(3).random((K, K))
+    Ma /= Ma.max()
+    P2, _ = synth.make_pairs(S, K, seed=4)
+    b = ops.sinkhorn_pairs(dev(P2), dev(Ma), 0.1, rng, precision="f32").cpu().numpy()
+    want2, _, _ = po.sinkhorn_rows(P2, Ma, 0.1, 0, S)
+    np.testing.assert_allclose(b, want2.ravel(), rtol=1e-4)
+
+
 @pytest.mark.parametrize("K", [12, 64])
 def test_sinkhorn_asymmetric_cost(K):
     """wasserstein_d accepts any cost matrix: a non-symmetric one keeps K0^T in shared memory."""
