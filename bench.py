@@ -299,14 +299,17 @@ def run_c5(args):
     got_e = dense_e[sub][:, sub]
     got_s = dense_s[sub][:, sub]
     emd_identical = bool(torch.equal(one_e, got_e))
+    sk_identical = bool(torch.equal(one_s, got_s))
     sk_rel = float(((one_s - got_s).abs() / one_s.abs()).max().item())
-    flags = torch.tensor([0.0 if emd_identical else 1.0, sk_rel], dtype=torch.float64, device="cuda")
+    flags = torch.tensor([0.0 if emd_identical else 1.0, sk_rel, 0.0 if sk_identical else 1.0], dtype=torch.float64,
+                         device="cuda")
     if world > 1:
         dist.all_reduce(flags, op=dist.ReduceOp.MAX)
     checks["partition_vs_single_rank"] = {
         "what": f"{sub.numel()} x {sub.numel()} sub-matrix of the {world}-rank all-gathered result vs the same "
                 "sub-cohort solved on one rank, on every rank",
-        "emd_bit_identical": bool(flags[0].item() == 0.0), "sinkhorn_max_rel_diff": float(flags[1].item())}
+        "emd_bit_identical": bool(flags[0].item() == 0.0), "sinkhorn_bit_identical": bool(flags[2].item() == 0.0),
+        "sinkhorn_max_rel_diff": float(flags[1].item())}
 
     if rank == 0:
         rs = np.random.default_rng(0)

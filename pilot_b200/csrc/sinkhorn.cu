@@ -99,7 +99,9 @@ extern "C" int pilot_sinkhorn_pairs(const double *props, int S, int K, const dou
     // few cell types: one warp per problem with K0 in registers (lowest latency per iteration, and
     // for 17..32 types also the higher throughput).  With <= 16 types half of its lanes idle, so a
     // large batch goes to the DMMA panels instead (measured: 400 K problems, K = 12: 5.6 vs 6.9 ms).
-    const bool warp_form = algo == 0 && K <= swk_max_k() && (K > 16 || pm.n_local < 200000);
+    // The choice depends on the COHORT size only (not on this rank's share or on the window), so that a problem is
+    // solved by the same arithmetic however the pair space is partitioned: results are partition-invariant bit for bit.
+    const bool warp_form = algo == 0 && K <= swk_max_k() && (K > 16 || (long long)S * S < 200000);
     if (warp_form) {  // symmetric cost only; an asymmetric one falls through to the general panels below
         rc = swk_launch(props, K, prm, pm, ws.setup, out, iters, absorptions, status, ws.counter_fast, ws.redo,
                         ws.n_redo, st);

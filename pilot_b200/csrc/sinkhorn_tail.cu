@@ -1,7 +1,15 @@
 // Kernel (3), tail of the DMMA-panel Sinkhorn solver: one warp per handed-over problem, continuing
 // from the exported scaled iterates (reference call site pilotpy/tools/Trajectory.py:513-515, POT
-// sinkhorn_stabilized schedule; same arithmetic as sinkhorn_warp.cu, K0 in shared memory because
-// 2 x 64 rows per lane do not fit the register file).
+// sinkhorn_stabilized schedule; K0 in shared memory because 2 x 64 rows per lane do not fit the
+// register file).
+//
+// BIT-IDENTICAL to the panels.  Which problems are handed over depends on timing, so the result of a
+// problem must not depend on where it finishes.  mma.sync.m8n8k4.f64 accumulates its four products as a
+// chain of FMAs in ascending k (measured: tools/dmma_order.cu, 0 mismatches in 128 000 entries), so a
+// panel matvec row is the sequential chain s = fma(K0[i][row], x[i], s), i = 0, 1, 2, ...; the matvecs here
+// run exactly that chain (two rows per lane), the marginal error is summed in the panels' order (rows
+// 8m + g ascending in m, then the g-butterfly 1, 2, 4) and the final cost uses the panels' code.  Two runs,
+// and runs on 1, 2, 4 or 8 GPUs, therefore give bit-identical Sinkhorn matrices.
 //
 // A panel of 8 problems costs ~6 us per iteration however few of its slots are still in use; the
 // stragglers of a batch (the problems that run to the 1000-iteration cap while the mean is ~55)
@@ -26,43 +34,34 @@ __device__ __forceinline__ double skt_div(double x, double y)
     return fma(q0, fma(e, e, e), q0);
 }
 
-// res[rr] = sum_i mat[i][row0 + rr] * buf[i]   (mat is [KP][KP], i-major; the lane's R rows are
-// adjacent, so R = 2 reads them with one 128-bit load; buf is broadcast as 128-bit loads)
+// res[rr] = sum_i mat[i][row0 + rr] * buf[i] as ONE fma chain in ascending i per row -- the order in which the
+// DMMA panels accumulate (see the header) -- (mat is [KP][KP], i-major; the lane's R rows are adjacent, so
+// R = 2 reads them with one 128-bit load; buf is broadcast as 128-bit loads)
 template <int KP, int R>
 __device__ __forceinline__ void skt_matvec(const double *__restrict__ mat, int row0, const double *buf,
                                            double (&res)[R])
 {
-    // 8 independent chains per row: the dependent DFMA latency (~18 cycles), not the issue rate,
-    // bounds a lone warp
-    double s[R][8];
+    double s[R];
 #pragma unroll
-    for (int rr = 0; rr < R; ++rr)
-#pragma unroll
-        for (int c = 0; c < 8; ++c) s[rr][c] = 0.0;
+    for (int rr = 0; rr < R; ++rr) s[rr] = 0.0;
     const double *m = mat + row0;
-#pragma unroll 2
-    for (int i = 0; i < KP; i += 8) {
-        double xs[8];
-#pragma unroll
-        for (int c = 0; c < 8; c += 2) {
-            const double2 x = *reinterpret_cast<const double2 *>(buf + i + c);
-            xs[c] = x.x;
-            xs[c + 1] = x.y;
-        }
-#pragma unroll
-        for (int c = 0; c < 8; ++c) {
-            if (R == 2) {
-                const double2 k = *reinterpret_cast<const double2 *>(m + (i + c) * KP);
-                s[0][c] = fma(k.x, xs[c], s[0][c]);
-                s[R - 1][c] = fma(k.y, xs[c], s[R - 1][c]);
-            } else {
-                s[0][c] = fma(m[(i + c) * KP], xs[c], s[0][c]);
-            }
+#pragma unroll 4
+    for (int i = 0; i < KP; i += 2) {
+        const double2 x = *reinterpret_cast<const double2 *>(buf + i);
+        if (R == 2) {
+            const double2 k0 = *reinterpret_cast<const double2 *>(m + i * KP);
+            const double2 k1 = *reinterpret_cast<const double2 *>(m + (i + 1) * KP);
+            s[0] = fma(k0.x, x.x, s[0]);
+            s[R - 1] = fma(k0.y, x.x, s[R - 1]);
+            s[0] = fma(k1.x, x.y, s[0]);
+            s[R - 1] = fma(k1.y, x.y, s[R - 1]);
+        } else {
+            s[0] = fma(m[i * KP], x.x, s[0]);
+            s[0] = fma(m[(i + 1) * KP], x.y, s[0]);
         }
     }
 #pragma unroll
-    for (int rr = 0; rr < R; ++rr)
-        res[rr] = ((s[rr][0] + s[rr][1]) + (s[rr][2] + s[rr][3])) + ((s[rr][4] + s[rr][5]) + (s[rr][6] + s[rr][7]));
+    for (int rr = 0; rr < R; ++rr) res[rr] = s[rr];
 }
 
 enum { SKT_PEND = 1, SKT_FORCE = 2, SKT_BAD = 4 };
@@ -92,7 +91,8 @@ sinkhorn_tail_kernel(const double *__restrict__ props, int K, SkParams prm, Pair
     }
     __syncthreads();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    double *ub = sbuf + (size_t)warp * 2 * KP, *vb = ub + KP;
+    double *ub = sbuf + (size_t)warp * 3 * KP, *vb = ub + KP, *db = vb + KP;
+    const int kc = (K + 7) & ~7;  // the panels' compute extent
     int row[R];
     bool in_pad[R], row_ok[R];
 #pragma unroll
@@ -141,13 +141,20 @@ sinkhorn_tail_kernel(const double *__restrict__ props, int K, SkParams prm, Pair
                 if (ctl & SKT_BAD) { status = -1; break; }
                 bool conv = false;
                 if (ctl & SKT_PEND) {
-                    double e2 = 0.0;
+                    // || vt o T - b ||^2 summed like the panels do: lane g takes rows g, 8 + g, ... in ascending
+                    // order, then the butterfly over g
 #pragma unroll
-                    for (int rr = 0; rr < R; ++rr) {
-                        const double d = row_ok[rr] ? fma(v[rr], T[rr], -b[rr]) : 0.0;
-                        e2 = fma(d, d, e2);
-                    }
-                    conv = sqrt(warp_sum_d(e2)) <= prm.stop_thr;
+                    for (int rr = 0; rr < R; ++rr)
+                        if (in_pad[rr]) db[row[rr]] = row_ok[rr] ? fma(v[rr], T[rr], -b[rr]) : 0.0;
+                    __syncwarp();
+                    double e2 = 0.0;
+                    for (int r8 = lane & 7; r8 < kc; r8 += 8)
+                        if (r8 < K) { const double d = db[r8]; e2 = fma(d, d, e2); }
+                    e2 += __shfl_xor_sync(0xffffffffu, e2, 1);
+                    e2 += __shfl_xor_sync(0xffffffffu, e2, 2);
+                    e2 += __shfl_xor_sync(0xffffffffu, e2, 4);
+                    conv = sqrt(e2) <= prm.stop_thr;
+                    __syncwarp();
                 }
                 if (conv) { status = PILOT_ST_CONVERGED; break; }
                 if (ctl & SKT_FORCE) { status = PILOT_ST_MAXITER; break; }
@@ -196,12 +203,23 @@ sinkhorn_tail_kernel(const double *__restrict__ props, int K, SkParams prm, Pair
             }
         }
         if (status >= 0) {
-            // cost = sum_j vt_j * sum_i (M o K0)_ij ut_i   (ub holds the current ut)
-            double W[R];
-            skt_matvec<KP, R>(sMK, row[0], ub, W);
-            double c = 0.0;
+            // cost = sum_j vt_j * sum_i (M o K0)_ij ut_i in the panels' order: lane = column j, even / odd rows in
+            // two chains (ub holds the current ut; vt may have been rescaled by an absorption since vb was written)
+            __syncwarp();
 #pragma unroll
-            for (int rr = 0; rr < R; ++rr) c = fma(v[rr], W[rr], c);
+            for (int rr = 0; rr < R; ++rr)
+                if (in_pad[rr]) vb[row[rr]] = v[rr];
+            __syncwarp();
+            double c = 0.0;
+            for (int j = lane; j < kc; j += 32) {
+                double w0 = 0.0, w1 = 0.0;
+                for (int i = 0; i + 1 < K; i += 2) {
+                    w0 = fma(sMK[i * KP + j], ub[i], w0);
+                    w1 = fma(sMK[(i + 1) * KP + j], ub[i + 1], w1);
+                }
+                if (K & 1) w0 = fma(sMK[(K - 1) * KP + j], ub[K - 1], w0);
+                c = fma(vb[j], w0 + w1, c);
+            }
             const double cost = warp_sum_d(c);
             if (lane == 0) {
                 out[w] = cost;
@@ -225,7 +243,7 @@ static int skt_launch_t(const double *props, int K, const SkParams &prm, const P
                         int *iters, int *absn, int *status, long long *redo, unsigned long long *n_redo,
                         cudaStream_t st)
 {
-    const size_t smem = sizeof(double) * ((size_t)(SYM ? 2 : 3) * KP * KP + (size_t)SKT_WARPS * 2 * KP);
+    const size_t smem = sizeof(double) * ((size_t)(SYM ? 2 : 3) * KP * KP + (size_t)SKT_WARPS * 3 * KP);
     PILOT_CUDA(cudaFuncSetAttribute(sinkhorn_tail_kernel<KP, SYM>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                     (int)smem));
     const double *K0 = setup, *K0T = K0 + KP * KP, *MK = K0T + KP * KP;

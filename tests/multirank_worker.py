@@ -1,6 +1,6 @@
 """Worker of tests/test_gpu_multirank.py (launched under torchrun, one rank per GPU, NCCL): the matrices
 assembled from the ranks' shares with the NCCL all-gather must equal a single-rank solve of the same
-problems entry by entry -- exact EMD bit-identical, Sinkhorn <= 1e-12 relative -- for the device path
+problems entry by entry, BIT FOR BIT, for both solvers -- for the device path
 (pairs.all_pairs), the banded host path (pairs.all_pairs_host) and the public tl.wasserstein_d."""
 import os
 import sys
@@ -27,14 +27,11 @@ def main():
             multi = pairs.all_pairs(Pd, Md, regularized, reg)
             single = pairs.all_pairs(Pd, Md, regularized, reg, single_rank=True)
             host, host_T = pairs.all_pairs_host(Pd, Md, regularized, reg, n_bands=5, with_transpose=True)
-            if regularized == "unreg":
-                assert torch.equal(multi, single), f"EMD differs between {world} ranks and 1 rank (S={S}, K={K})"
-                assert np.array_equal(host, single.cpu().numpy())
-            else:
-                rel = float(((multi - single).abs() / single.abs()).max().item())
-                worst = max(worst, rel)
-                assert rel <= 1e-12, f"Sinkhorn differs by {rel} between {world} ranks and 1 rank"
-                np.testing.assert_allclose(host, single.cpu().numpy(), rtol=1e-12)
+            rel = float(((multi - single).abs() / single.abs().clamp_min(1e-300)).max().item())
+            worst = max(worst, rel)
+            assert torch.equal(multi, single), \
+                f"{regularized}: {world} ranks and 1 rank differ (max rel {rel}, S={S}, K={K})"
+            assert np.array_equal(host, single.cpu().numpy())
             assert np.array_equal(host_T, host.T)
             # every rank holds the same matrix
             ref = multi.clone()
@@ -50,7 +47,7 @@ def main():
             assert np.array_equal(df.to_numpy(), EMD.T)
     dist.barrier()
     if rank == 0:
-        print(f"MULTIRANK OK world={world} sinkhorn_worst_rel={worst:.3e}", flush=True)
+        print(f"MULTIRANK OK world={world} worst_rel_diff={worst:.3e}", flush=True)
     dist.destroy_process_group()
 
 
