@@ -4,15 +4,14 @@
 // NaNs ignored, even counts -> (lo + hi) / 2 rounded in the input dtype).
 //
 // Two exact paths:
-//  * sampled-pivot streaming path (default for n >= 64K): a block-strided sample of rows gives,
-//    per (type, dim), two pivots lo <= hi that bracket the median with ~1e-7 failure odds;
-//    ONE coalesced streaming pass over X then counts x < lo, x == lo, x == hi in warp-private
-//    shared-memory tables (no atomics: lane = dimension, so a warp never collides with itself)
-//    and appends the few elements with lo < x < hi (~10 %) to per-pair candidate lists; a
-//    one-CTA-per-pair kernel finishes the selection inside the candidates.  If a pair's rank
-//    falls outside its bracket (or its list overflows) the same CTA falls back to an exact
-//    radix select over the full column -- no host round trip, results are always exact.
-//    HBM traffic: one read of X + ~12 % for the sample + the candidate lists (L2 resident).
+//  * sampled-pivot streaming path in natural row order (default for n >= 64K; second half of this file):
+//    a hashed sample of ~2048 rows per type gives, per (type, dim), two pivots lo <= hi that bracket the
+//    median with ~4e-8 failure odds; ONE coalesced pass over X in memory order then counts x < lo and
+//    x > hi in shared-memory counters and appends the ~12 % of elements inside the bracket to per-pair
+//    lists; a one-CTA-per-pair kernel finishes the selection inside the list.  If a pair's rank falls
+//    outside its bracket (or its list overflows) the same CTA falls back to an exact radix select over
+//    the type's rows -- no host round trip, results are always exact.
+//    HBM traffic: one read of X + ~6 % for the sample + the lists (written once, read once).
 //  * most-significant-digit radix select (small inputs, huge K*D): every pass streams X once
 //    and histograms the current 8-bit digit of the elements whose higher digits match the
 //    running prefix of their (type, dim) query; 4 passes for f32, 8 for f64.
@@ -226,15 +225,33 @@ static int median_run(const T *X, long long n, int D, long long ldx, const int *
 
 
 // =====================================================================================
-// sampled-pivot streaming path over TYPE-SORTED row tiles
+// sampled-pivot streaming path in NATURAL row order
 // =====================================================================================
-constexpr int MED_SCAP = 2048;          // samples per (type, dim) for the pivots
+// Five small kernels around ONE coalesced pass over X:
+//   count   : cells per type (shared-memory histogram of the codes)
+//   plan    : per type the sampling stride, the candidate-list capacity and its offset in the pool
+//   sample  : ~2048 hashed rows per type copied into a type-major sample buffer (about 6 % of X)
+//   pivot   : per (type, dim) two pivots lo <= hi at the sample ranks n_s/2 -+ 2.75 sqrt(n_s): the true median
+//             lies outside with probability ~4e-8; the bracket holds ~12 % of the type's values
+//   stream  : X is read exactly once, in memory order (consecutive threads = consecutive elements, rows of any
+//             length or alignment coalesce); the pivots of every (type, dim) sit in shared memory; an element
+//             below lo / above hi bumps a shared-memory counter (lanes of a warp hit different dims: no
+//             conflicts), an element inside the closed bracket (or NaN) is appended to its (type, dim) list
+//             through one global atomic on the list cursor (~12 % of the elements; the cursors are L2 resident)
+//   finish  : one CTA per (type, dim): rank bookkeeping (below / tie plateau / list / above), NaN count and radix
+//             select inside the list staged in shared memory; if the rank fell outside the bracket or the list
+//             overflowed, the same CTA runs an exact radix select over the type's rows -- no host round trip
+// Versus round 1 (rows gathered in type-sorted order): no counting sort of the row ids, no 200-byte row gathers
+// (which cost 1.35x the algorithmic bytes in partial sectors), three kernels fewer.
+constexpr int MN_SAMPLE_MIN = 2048;     // target sample rows per type: n_k / 16 clamped to [MIN, MAX]
+constexpr int MN_SAMPLE_MAX = 8192;     //   (bracket width ~ 5.5 / sqrt(sample): 12 % ... 6 % of the type's values)
+constexpr int MN_MCAP = MN_SAMPLE_MAX + MN_SAMPLE_MAX / 4;  // most sample rows a type can hold (pivot kernel's buffer)
 constexpr double MED_SIGMAS = 5.5;      // half-width of the bracket in binomial sigmas
-constexpr int MS_PROC = 4;              // tile processors (64 threads) per stream CTA
-constexpr int MS_MAXCH = 4;             // column chunks of 64 per processor -> D <= 256
-constexpr int MS_STAGE_BYTES = 32768;   // candidates staged in shared memory by the finish kernel
-constexpr int MS_MAXITEMS_PER_TYPE = 2048;
-constexpr int MS_FIN_THREADS = 256;
+constexpr int MN_THREADS = 512;         // stream kernel
+constexpr int MN_FIN_THREADS = 256;
+constexpr int MN_REP = 32;              // replicas of every (type, dim) list: same-address global atomics serialise at ~20 ns
+constexpr int MN_STAGE_BYTES = 65536;   // candidates staged in shared memory by the finish kernel
+constexpr size_t MN_SMEM_MAX = 160 * 1024;  // pivots + counters of every (type, dim) must fit
 
 // shared-memory reduction without the compiler's warp-aggregation collective
 __device__ __forceinline__ void red_shared_inc(unsigned int *p)
@@ -247,27 +264,26 @@ template <typename T> struct Inf;
 template <> struct Inf<float> { __device__ static float pos() { return __int_as_float(0x7f800000); } };
 template <> struct Inf<double> { __device__ static double pos() { return __longlong_as_double(0x7ff0000000000000LL); } };
 
-// workspace header (first 64 bytes, zeroed per call)
-struct MsHeader {
-    unsigned int fail;          // pairs that took the exact full-column fallback (diagnostic)
-    unsigned int item_counter;  // work queue of the stream kernel
-    unsigned int n_items;
-    unsigned int pad[13];
+
+struct MnHeader {
+    unsigned int fail;  // pairs that took the exact full-column fallback (diagnostic, first word of the workspace)
+    unsigned int pad[63];
 };
 
-template <typename T> struct MsWs {
-    MsHeader *hdr;
-    unsigned int *cursor;      // K: scatter reservation cursors
-    unsigned long long *type_cnt;  // K
-    unsigned int *type_off;    // K + 1
-    int *item_first;           // K + 1
-    int *item_k;               // NI
-    unsigned int *item_r0, *item_r1;  // NI: range inside sorted_rows
-    unsigned int *sorted_rows; // n
-    T *piv;                    // KD x 2
-    unsigned int *cnt;         // NI x D x 5: below, eq_lo, eq_hi, nan, ncand
-    T *cand;                   // NI x D x capi
-    unsigned int item_rows, capi, ni_max;
+template <typename T> struct MnWs {
+    MnHeader *hdr;
+    unsigned long long *type_cnt;          // K
+    unsigned int *samp_cur;                // K: rows in the type's sample buffer
+    unsigned int *below, *above;           // KD each: values below the bracket; values ON a tie plateau lo == hi
+    unsigned int *ncand;                   // MN_REP x KD list cursors
+    unsigned long long *cand_off;          // K: element offset of the type's candidate block; list (rep, d) at + (rep * D + d) * cap
+    unsigned int *cap;                     // K: capacity of ONE replica list of a (type, dim)
+    unsigned int *sstride;                 // K: keep a row when hash(row) % sstride == 0
+    unsigned int *scap;                    // K: rows of the type's sample buffer
+    unsigned long long *samp_off;          // K: first row of the type's sample buffer
+    T *piv;                                // KD x 2
+    T *samp;                               // per type a block of D x scap[k] values, dim-major
+    T *cand;                               // pool
 };
 
 __global__ void msort_count_kernel(const int *__restrict__ code, long long n, int K,
@@ -286,65 +302,99 @@ __global__ void msort_count_kernel(const int *__restrict__ code, long long n, in
         if (s_cnt[i]) atomicAdd(&type_cnt[i], (unsigned long long)s_cnt[i]);
 }
 
-// one CTA: type offsets and the work items (type, row range) of the stream kernel
-template <typename T>
-__global__ void __launch_bounds__(256) msort_plan_kernel(int K, MsWs<T> ws)
+
+template <typename T> __global__ void mn_plan_kernel(int K, int D, MnWs<T> ws)
 {
-    if (threadIdx.x == 0) {
-        unsigned off = 0;
-        int ni = 0;
-        for (int k = 0; k < K; ++k) {
-            const unsigned nk = (unsigned)ws.type_cnt[k];
-            ws.type_off[k] = off;
-            ws.item_first[k] = ni;
-            ni += (int)((nk + ws.item_rows - 1) / ws.item_rows);
-            off += nk;
-        }
-        ws.type_off[K] = off;
-        ws.item_first[K] = ni;
-        ws.hdr->n_items = (unsigned)ni;
-    }
-    __syncthreads();
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    unsigned long long off = 0, soff = 0;
     for (int k = 0; k < K; ++k) {
-        const unsigned off = ws.type_off[k], nk = ws.type_off[k + 1] - off;
-        const int first = ws.item_first[k], cnt = ws.item_first[k + 1] - first;
-        for (int j = threadIdx.x; j < cnt; j += blockDim.x) {
-            const unsigned r = (unsigned)j * ws.item_rows;
-            ws.item_k[first + j] = k;
-            ws.item_r0[first + j] = off + r;
-            ws.item_r1[first + j] = off + (r + ws.item_rows < nk ? r + ws.item_rows : nk);
-        }
+        const unsigned long long nk = ws.type_cnt[k];
+        const unsigned cap = (unsigned)(0.35 * (double)nk / MN_REP) + 64u;
+        unsigned long long target = nk / 16;
+        target = target < MN_SAMPLE_MIN ? MN_SAMPLE_MIN : (target > MN_SAMPLE_MAX ? MN_SAMPLE_MAX : target);
+        const unsigned long long sst = (nk + target - 1) / target;
+        ws.sstride[k] = (unsigned)(sst > 1 ? sst : 1);
+        const unsigned long long expect = nk / (sst > 1 ? sst : 1);
+        unsigned long long sc = expect + expect / 4 + 64;  // > 10 sigma of the binomial above the expectation
+        if (sc > MN_MCAP) sc = MN_MCAP;
+        ws.scap[k] = (unsigned)sc;
+        ws.samp_off[k] = soff;
+        soff += sc;
+        ws.cap[k] = cap;
+        ws.cand_off[k] = off;
+        off += (unsigned long long)cap * (unsigned)D * MN_REP;
     }
 }
 
-// counting-sort scatter of the row ids by type: CTA-local histogram, one global reservation per
-// (CTA, type), shared-memory cursors for the positions inside the reservation
+// replica of a row's candidate lists: consecutive rows take consecutive replicas, with two folds against periods
+__device__ __forceinline__ unsigned mn_rep(unsigned row) { return (row + (row >> 5) + (row >> 10)) & (MN_REP - 1); }
+
+__device__ __forceinline__ unsigned mn_hash(unsigned i)
+{
+    unsigned h = i * 0x9E3779B1u;
+    h ^= h >> 15;
+    h *= 0x85EBCA77u;
+    h ^= h >> 13;
+    return h;
+}
+
+// hashed row sample, type-major.  A CTA walks its contiguous block of rows, collects the selected ones in shared
+// memory (position inside the CTA's share of the type through a shared-memory atomic), reserves its share of every
+// type's sample buffer with ONE global atomic per type, then copies the rows (coalesced D-element rows).
+constexpr int MN_SAMP_STAGE = 3072;  // selected rows a CTA can stage
 template <typename T>
 __global__ void __launch_bounds__(256)
-msort_scatter_kernel(const int *__restrict__ code, long long n, int K, MsWs<T> ws)
+mn_sample_kernel(const T *__restrict__ X, long long n, int D, long long ldx, const int *__restrict__ code, int K,
+                 MnWs<T> ws)
 {
-    extern __shared__ unsigned int s_u[];  // hist[K], base[K]
-    unsigned int *hist = s_u, *base = s_u + K;
-    for (int i = threadIdx.x; i < K; i += blockDim.x) hist[i] = 0u;
-    __syncthreads();
+    extern __shared__ unsigned int s_u[];  // cnt[K], base[K]
+    unsigned int *s_cnt = s_u, *s_base = s_u + K;
+    __shared__ unsigned int s_row[MN_SAMP_STAGE];
+    __shared__ unsigned int s_kp[MN_SAMP_STAGE];  // type << 16 | position inside the CTA's share
+    __shared__ unsigned int s_n;
     const long long per = (n + gridDim.x - 1) / gridDim.x;
     const long long c0 = (long long)blockIdx.x * per, c1 = c0 + per < n ? c0 + per : n;
-    for (long long i = c0 + threadIdx.x; i < c1; i += blockDim.x) {
-        const int k = __ldg(code + i);
-        if ((unsigned)k < (unsigned)K) atomicAdd(&hist[k], 1u);
-    }
-    __syncthreads();
-    for (int i = threadIdx.x; i < K; i += blockDim.x) {
-        base[i] = hist[i] ? ws.type_off[i] + atomicAdd(&ws.cursor[i], hist[i]) : 0u;
-        hist[i] = 0u;
-    }
-    __syncthreads();
-    for (long long i = c0 + threadIdx.x; i < c1; i += blockDim.x) {
-        const int k = __ldg(code + i);
-        if ((unsigned)k < (unsigned)K) {
-            const unsigned pos = atomicAdd(&hist[k], 1u);
-            ws.sorted_rows[base[k] + pos] = (unsigned)i;
+    for (long long t0 = c0; t0 < c1; t0 += 32768) {  // in rounds, so that the stage cannot overflow
+        const long long t1 = t0 + 32768 < c1 ? t0 + 32768 : c1;
+        for (int i = threadIdx.x; i < K; i += blockDim.x) s_cnt[i] = 0u;
+        if (threadIdx.x == 0) s_n = 0u;
+        __syncthreads();
+        for (long long i = t0 + threadIdx.x; i < t1; i += blockDim.x) {
+            const int k = __ldg(code + i);
+            if ((unsigned)k < (unsigned)K) {
+                const unsigned sst = ws.sstride[k];
+                if (sst <= 1u || (mn_hash((unsigned)i) % sst) == 0u) {
+                    const unsigned lp = atomicAdd(&s_cnt[k], 1u);
+                    const unsigned e = atomicAdd(&s_n, 1u);
+                    if (e < (unsigned)MN_SAMP_STAGE && lp < 65536u) {
+                        s_row[e] = (unsigned)i;
+                        s_kp[e] = ((unsigned)k << 16) | lp;
+                    }
+                }
+            }
         }
+        __syncthreads();
+        for (int i = threadIdx.x; i < K; i += blockDim.x)
+            s_base[i] = s_cnt[i] ? atomicAdd(&ws.samp_cur[i], s_cnt[i]) : 0u;
+        __syncthreads();
+        const unsigned ne = s_n < (unsigned)MN_SAMP_STAGE ? s_n : (unsigned)MN_SAMP_STAGE;
+        // copy: thread t moves the elements t, t + 256, ... of the staged rows (row-major): consecutive threads read
+        // consecutive elements of a row, and every load is independent of the others
+        {
+            const unsigned total = ne * (unsigned)D;
+            unsigned e = threadIdx.x / (unsigned)D, d = threadIdx.x % (unsigned)D;
+            const unsigned se = blockDim.x / (unsigned)D, sd = blockDim.x % (unsigned)D;
+            for (unsigned idx = threadIdx.x; idx < total; idx += blockDim.x) {
+                const unsigned kp = s_kp[e];
+                const unsigned k = kp >> 16, pos = s_base[k] + (kp & 0xffffu);
+                const unsigned scp = ws.scap[k];
+                // dim-major inside the type's block: the pivot kernel reads its column contiguously
+                if (pos < scp) ws.samp[ws.samp_off[k] * D + (size_t)d * scp + pos] = X[(long long)s_row[e] * ldx + d];
+                d += sd; e += se;
+                if (d >= (unsigned)D) { d -= D; ++e; }
+            }
+        }
+        __syncthreads();
     }
 }
 
@@ -412,42 +462,30 @@ __device__ void cta_select2_raw(Src src, long long r0, long long r1, unsigned in
     out1 = KO::value(p1);
 }
 
-// one CTA per (type, dim): pivots lo <= hi bracketing the median, from <= MED_SCAP evenly spaced rows
-// of the type's sorted segment, gathered once into shared memory
+
+// one CTA per (type, dim): pivots lo <= hi bracketing the median, from the type's sample rows
 template <typename T>
 __global__ void __launch_bounds__(256)
-msort_pivot_kernel(const T *__restrict__ X, int D, long long ldx, MsWs<T> ws)
+mn_pivot_kernel(int D, MnWs<T> ws)
 {
     using KO = KeyOf<T>;
     using Key = typename KO::type;
     constexpr int BITS = sizeof(Key) * 8;
     __shared__ unsigned int hist[512];
     __shared__ long long sh[4];
-    __shared__ T vals[MED_SCAP];
+    extern __shared__ __align__(16) unsigned char pv_raw[];
+    T *vals = reinterpret_cast<T *>(pv_raw);  // MN_MCAP
     const int kd = blockIdx.x;
     const int k = kd / D, d = kd - k * D;
-    const unsigned off = ws.type_off[k];
-    const unsigned long long Nk = ws.type_off[k + 1] - off;
-    const int ns = (int)(Nk < (unsigned long long)MED_SCAP ? Nk : (unsigned long long)MED_SCAP);
+    const unsigned cur = ws.samp_cur[k], scp = ws.scap[k];
+    const int ns = (int)(cur < scp ? cur : scp);
     T lo = -Inf<T>::pos(), hi = Inf<T>::pos();
     if (ns >= 64) {
         const int delta = (int)ceil(0.5 * MED_SIGMAS * sqrt((double)ns)) + 1;
         const int jlo = (ns - 1) / 2 - delta, jhi = ns / 2 + delta;
         if (jlo > 0 && jhi < ns - 1) {
-            const T *Xd = X + d;
-            for (int i0 = threadIdx.x; i0 < ns; i0 += 4 * 256) {
-                unsigned rid[4];
-#pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    const int i = i0 + 256 * u;
-                    rid[u] = i < ns ? ws.sorted_rows[off + (unsigned)(((unsigned long long)i * Nk) / (unsigned)ns)] : 0u;
-                }
-#pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    const int i = i0 + 256 * u;
-                    if (i < ns) vals[i] = Xd[(long long)rid[u] * ldx];
-                }
-            }
+            const T *col = ws.samp + ws.samp_off[k] * D + (size_t)d * scp;
+            for (int i = threadIdx.x; i < ns; i += 256) vals[i] = col[i];
             __syncthreads();
             auto smp = [&](auto f) {
                 for (int i = threadIdx.x; i < ns; i += 256) f(vals[i]);
@@ -464,230 +502,276 @@ msort_pivot_kernel(const T *__restrict__ X, int D, long long ldx, MsWs<T> ws)
     }
 }
 
-template <int BYTES> __device__ __forceinline__ void cp_async_bytes(unsigned smem_addr, const void *src)
-{
-    if (BYTES == 16) asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_addr), "l"(src) : "memory");
-    else if (BYTES == 8) asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_addr), "l"(src) : "memory");
-    else asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_addr), "l"(src) : "memory");
-}
-
-// The streaming pass.  A tile processor (64 threads) takes work items = (type, <= item_rows rows of
-// that type); rows are gathered with cp.async into a double-buffered shared-memory tile (each row is
-// one contiguous D-element read), then THREAD = COLUMN: the pivots of (type, d) and three counters
-// (below, above, listed) live in registers; everything inside the closed bracket, and every NaN,
-// goes to the thread's private list through a predicated store.  No atomics, no ballots, no tables,
-// two compares per element.
-template <typename T, int VB>  // VB = bytes per cp.async (row starts and D * sizeof(T) are multiples of it)
-__global__ void __launch_bounds__(MS_PROC * 64)
-msort_stream_kernel(const T *__restrict__ X, int D, long long ldx, int TR, MsWs<T> ws)
+// The streaming pass: X once, in memory order.
+template <typename T>
+__global__ void __launch_bounds__(MN_THREADS)
+mn_stream_kernel(const T *__restrict__ X, long long n, int D, long long ldx, const int *__restrict__ code, int K,
+                 MnWs<T> ws)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    __shared__ unsigned int s_item[MS_PROC];
-    const int proc = threadIdx.x >> 6, ptid = threadIdx.x & 63, pw = ptid >> 5, lane = threadIdx.x & 31;
-    T *tile = reinterpret_cast<T *>(smem_raw) + (size_t)proc * 2 * TR * D;  // [2][TR][D]
-    const unsigned tile_s = (unsigned)__cvta_generic_to_shared(tile);
-    const unsigned n_items = ws.hdr->n_items;
-    const unsigned capi = ws.capi;
-    const int row_bytes = D * (int)sizeof(T);
-    const int nvec = row_bytes / VB;  // cp.async chunks per row
-    for (;;) {
-        if (ptid == 0) s_item[proc] = atomicAdd(&ws.hdr->item_counter, 1u);
-        asm volatile("bar.sync %0, 64;" ::"r"(proc + 1) : "memory");
-        const unsigned it = s_item[proc];
-        asm volatile("bar.sync %0, 64;" ::"r"(proc + 1) : "memory");
-        if (it >= n_items) break;
-        const int k = ws.item_k[it];
-        const unsigned r0 = ws.item_r0[it], r1 = ws.item_r1[it];
-        T lo[MS_MAXCH], hi[MS_MAXCH];
-        unsigned c_below[MS_MAXCH], c_above[MS_MAXCH], c_cand[MS_MAXCH];
-#pragma unroll
-        for (int ch = 0; ch < MS_MAXCH; ++ch) {
-            const int d = ch * 64 + ptid;
-            lo[ch] = d < D ? ws.piv[2 * ((size_t)k * D + d)] : (T)0;
-            hi[ch] = d < D ? ws.piv[2 * ((size_t)k * D + d) + 1] : (T)0;
-            c_below[ch] = c_above[ch] = c_cand[ch] = 0u;
+    const int KD = K * D;
+    T *spiv = reinterpret_cast<T *>(smem_raw);                                  // [KD][2]
+    unsigned long long *scoff = reinterpret_cast<unsigned long long *>(spiv + 2 * (size_t)KD);  // [K]
+    unsigned int *sbelow = reinterpret_cast<unsigned int *>(scoff + K);         // [KD]
+    unsigned int *sabove = sbelow + KD;                                         // [KD]
+    unsigned int *scap = sabove + KD;                                           // [K]
+    for (int i = threadIdx.x; i < 2 * KD; i += blockDim.x) spiv[i] = ws.piv[i];
+    for (int i = threadIdx.x; i < KD; i += blockDim.x) { sbelow[i] = 0u; sabove[i] = 0u; }
+    for (int i = threadIdx.x; i < K; i += blockDim.x) { scoff[i] = ws.cand_off[i]; scap[i] = ws.cap[i]; }
+    __syncthreads();
+
+    // this CTA's contiguous block of rows; thread t takes its elements t, t + NT, t + 2 NT, ... (row-major)
+    const long long per = (n + gridDim.x - 1) / gridDim.x;
+    const long long r0 = (long long)blockIdx.x * per;
+    const long long r1 = r0 + per < n ? r0 + per : n;
+    const int NT = blockDim.x;
+    long long row = r0 + threadIdx.x / D;
+    int d = threadIdx.x % D;
+    const int step_r = NT / D, step_d = NT % D;
+
+    auto handle = [&](int k, int dd, T x, long long rrow) {
+        if ((unsigned)k >= (unsigned)K) return;
+        const int kd = k * D + dd;
+        const T lo = spiv[2 * kd], hi = spiv[2 * kd + 1];
+        if (x < lo) {
+            red_shared_inc(&sbelow[kd]);
+        } else if (x > hi) {
+            // above the bracket: nothing to count (above = n_k - below - ties - listed)
+        } else if (lo == hi && x == lo) {
+            red_shared_inc(&sabove[kd]);  // the tie plateau (this array holds the tie counts)
+        } else {
+            // the closed bracket [lo, hi] and every NaN go to the list; with lo == hi (the sample saw a plateau
+            // of ties) the ties are counted, not listed
+            const unsigned rep = mn_rep((unsigned)rrow);  // by row, not by CTA: balanced for any row order
+            const unsigned pos = atomicAdd(&ws.ncand[(size_t)rep * KD + kd], 1u);
+            const unsigned cap = scap[k];
+            if (pos < cap) ws.cand[scoff[k] + ((size_t)rep * D + dd) * cap + pos] = x;
         }
-        const int ntiles = (int)((r1 - r0 + TR - 1) / TR);
-        auto load_tile = [&](int t, int buf) {
-            const unsigned rb = r0 + (unsigned)t * TR;
-            const unsigned rid_mine = (rb + lane < r1 && lane < TR) ? ws.sorted_rows[rb + lane] : 0u;
-            const unsigned dst = tile_s + (unsigned)(buf * TR) * row_bytes;
-            const int nrow = (int)(r1 - rb < (unsigned)TR ? r1 - rb : (unsigned)TR);
-            for (int row = pw; row < nrow; row += 2) {
-                const unsigned rid = __shfl_sync(0xffffffffu, rid_mine, row);
-                const char *src = reinterpret_cast<const char *>(X + (long long)rid * ldx);
-                for (int c = lane; c < nvec; c += 32) cp_async_bytes<VB>(dst + row * row_bytes + c * VB, src + c * VB);
-            }
-            asm volatile("cp.async.commit_group;" ::: "memory");
-        };
-        load_tile(0, 0);
-        for (int t = 0; t < ntiles; ++t) {
-            const int buf = t & 1;
-            if (t + 1 < ntiles) {
-                load_tile(t + 1, buf ^ 1);
-                asm volatile("cp.async.wait_group 1;" ::: "memory");
-            } else {
-                asm volatile("cp.async.wait_group 0;" ::: "memory");
-            }
-            asm volatile("bar.sync %0, 64;" ::"r"(proc + 1) : "memory");
-            const unsigned rb = r0 + (unsigned)t * TR;
-            const int rows = (int)(r1 - rb < (unsigned)TR ? r1 - rb : (unsigned)TR);
-            const T *src = tile + (size_t)buf * TR * D;
+    };
+
+    constexpr int U = 4;  // independent loads in flight per thread
+    while (row < r1) {
+        long long rr[U];
+        int dd[U], kk[U];
+        T xx[U];
 #pragma unroll
-            for (int ch = 0; ch < MS_MAXCH; ++ch) {
-                const int d = ch * 64 + ptid;
-                if (d < D) {
-                    T *cl = ws.cand + ((size_t)it * D + d) * capi;
-                    const T l = lo[ch], h = hi[ch];
-                    // lo == hi: the sample saw a plateau of ties -- they are counted (everything that is
-                    // neither below nor above nor stored), not stored; x != NaN is true for every x
-                    const T tie = l == h ? l : (T)NAN;
-                    unsigned nb = c_below[ch], na = c_above[ch], nc = c_cand[ch];
-                    const T *col = src + d;
-#pragma unroll 4
-                    for (int row = 0; row < rows; ++row) {
-                        const T x = col[row * D];
-                        const bool lt = x < l, gt = x > h;
-                        nb += lt ? 1u : 0u;
-                        na += gt ? 1u : 0u;
-                        // the closed bracket [lo, hi] and every NaN go to the list
-                        const bool st = !lt && !gt && x != tie;
-                        if (st && nc < capi) cl[nc] = x;
-                        nc += st ? 1u : 0u;
-                    }
-                    c_below[ch] = nb; c_above[ch] = na; c_cand[ch] = nc;
-                }
-            }
-            asm volatile("bar.sync %0, 64;" ::"r"(proc + 1) : "memory");  // tile buffer free again
+        for (int u = 0; u < U; ++u) {
+            rr[u] = row;
+            dd[u] = d;
+            d += step_d;
+            row += step_r;
+            if (d >= D) { d -= D; ++row; }
         }
 #pragma unroll
-        for (int ch = 0; ch < MS_MAXCH; ++ch) {
-            const int d = ch * 64 + ptid;
-            if (d < D) {
-                unsigned int *o = ws.cnt + ((size_t)it * D + d) * 5;
-                o[0] = c_below[ch]; o[1] = c_above[ch]; o[4] = c_cand[ch];
-            }
+        for (int u = 0; u < U; ++u) {
+            const bool ok = rr[u] < r1;
+            kk[u] = ok ? __ldg(code + rr[u]) : -1;
+            xx[u] = ok ? X[rr[u] * ldx + dd[u]] : (T)0;
         }
+#pragma unroll
+        for (int u = 0; u < U; ++u) handle(kk[u], dd[u], xx[u], rr[u]);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < KD; i += blockDim.x) {
+        const unsigned b = sbelow[i], a = sabove[i];
+        if (b) atomicAdd(&ws.below[i], b);
+        if (a) atomicAdd(&ws.above[i], a);
     }
 }
 
-// one CTA per (type, dim): rank bookkeeping over the type's items (below / tie plateau / lists /
-// above), NaN count and selection inside the lists, exact fallback over the type's own rows when the
-// bracket missed or a list overflowed
+// The streaming pass, fast path (rows contiguous, X 16-byte aligned): 128-bit loads, and the bracket candidates of a
+// warp are first compacted into a per-warp ring in shared memory and then appended 32 at a time with every lane
+// busy -- the divergent one-candidate-in-eight path of the scalar kernel cost more than the rest of the loop.
+constexpr int MN_RING = 256;  // entries per warp (an iteration adds at most 32 * 4)
 template <typename T>
-__global__ void __launch_bounds__(MS_FIN_THREADS)
-msort_finish_kernel(const T *__restrict__ X, int D, long long ldx, MsWs<T> ws, T *__restrict__ cent,
-                    double *__restrict__ cent64)
+__global__ void __launch_bounds__(MN_THREADS)
+mn_stream_vec_kernel(const T *__restrict__ X, long long n, int D, const int *__restrict__ code, int K, MnWs<T> ws)
+{
+    constexpr int V = 16 / (int)sizeof(T);  // elements per 128-bit load
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int KD = K * D;
+    T *spiv = reinterpret_cast<T *>(smem_raw);                                  // [KD][2]
+    unsigned long long *scoff = reinterpret_cast<unsigned long long *>(spiv + 2 * (size_t)KD);  // [K]
+    unsigned int *sbelow = reinterpret_cast<unsigned int *>(scoff + K);         // [KD]
+    unsigned int *sties = sbelow + KD;                                          // [KD]
+    unsigned int *scap = sties + KD;                                            // [K]
+    T *rval = reinterpret_cast<T *>(scap + K + (K & 1));                        // [warps][MN_RING]
+    unsigned int *rkey = reinterpret_cast<unsigned int *>(rval + (MN_THREADS / 32) * MN_RING);
+    for (int i = threadIdx.x; i < 2 * KD; i += blockDim.x) spiv[i] = ws.piv[i];
+    for (int i = threadIdx.x; i < KD; i += blockDim.x) { sbelow[i] = 0u; sties[i] = 0u; }
+    for (int i = threadIdx.x; i < K; i += blockDim.x) { scoff[i] = ws.cand_off[i]; scap[i] = ws.cap[i]; }
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const unsigned lt_mask = (1u << lane) - 1u;
+    T *wval = rval + warp * MN_RING;
+    unsigned int *wkey = rkey + warp * MN_RING;
+    unsigned head = 0, count = 0;  // warp-uniform ring state
+
+    // append the first `m` (<= 32) ring entries: one lane per candidate
+    auto flush32 = [&](unsigned m) {
+        if ((unsigned)lane < m) {
+            const unsigned at = (head + lane) & (MN_RING - 1);
+            const unsigned key = wkey[at];
+            const T x = wval[at];
+            const unsigned k = key & 0xfffu, dd = (key >> 12) & 0xfffu, rep = key >> 24;
+            const unsigned kd = k * (unsigned)D + dd;
+            const unsigned pos = atomicAdd(&ws.ncand[(size_t)rep * KD + kd], 1u);
+            const unsigned cap = scap[k];
+            if (pos < cap) ws.cand[scoff[k] + (size_t)(rep * (unsigned)D + dd) * cap + pos] = x;
+        }
+        head += m;
+        count -= m;
+    };
+
+    const long long E = n * (long long)D;
+    const long long Q = (E + V - 1) / V;
+    const long long per = (Q + gridDim.x - 1) / gridDim.x;
+    const long long q0 = (long long)blockIdx.x * per;
+    const long long q1 = q0 + per < Q ? q0 + per : Q;
+    const int NT = blockDim.x;
+    long long e = (q0 + threadIdx.x) * V;
+    long long row = e / D;
+    int d = (int)(e - row * D);
+    const int step_r = (NT * V) / D, step_d = (NT * V) % D;
+    const long long e_end = q1 * V < E ? q1 * V : E;
+    // every warp runs the same number of iterations (the ballots need all lanes)
+    const long long iters = (q1 - q0 + NT - 1) / NT;
+    for (long long it = 0; it < iters; ++it) {
+        T x[V];
+        const bool in = e + V <= e_end;
+        if (in) {
+            const int4 raw = *reinterpret_cast<const int4 *>(X + e);
+            if (V == 4) {
+                x[0] = (T)__int_as_float(raw.x); x[1] = (T)__int_as_float(raw.y);
+                x[V - 2] = (T)__int_as_float(raw.z); x[V - 1] = (T)__int_as_float(raw.w);
+            } else {
+                x[0] = (T)__hiloint2double(raw.y, raw.x);
+                x[V - 1] = (T)__hiloint2double(raw.w, raw.z);
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < V; ++j) x[j] = e + j < e_end ? X[e + j] : (T)0;
+        }
+        const bool any = e < e_end;
+        const int k0 = any ? __ldg(code + row) : -1;
+        const int wrap_at = D - d;  // elements j >= wrap_at belong to the next row
+        const int k1 = (any && wrap_at < V && row + 1 < n) ? __ldg(code + row + 1) : -1;
+        const unsigned rep0 = mn_rep((unsigned)row) << 24, rep1 = mn_rep((unsigned)row + 1u) << 24;
+        const int nvalid = in ? V : (any ? (int)(e_end - e) : 0);
+#pragma unroll
+        for (int j = 0; j < V; ++j) {
+            const bool w = j >= wrap_at;
+            const int dj = w ? d + j - D : d + j;
+            const int kj = w ? k1 : k0;
+            const bool valid = j < nvalid && (unsigned)kj < (unsigned)K;
+            const int kd = valid ? kj * D + dj : 0;
+            const T lo = spiv[2 * kd], hi = spiv[2 * kd + 1];
+            const bool lt = x[j] < lo, ge = !(x[j] > hi);
+            if (valid && lt) red_shared_inc(&sbelow[kd]);
+            bool cand = valid && !lt && ge;              // the closed bracket [lo, hi] and every NaN ...
+            if (cand && lo == hi && x[j] == lo) {        // ... except the ties of a plateau lo == hi: counted
+                red_shared_inc(&sties[kd]);
+                cand = false;
+            }
+            const unsigned bal = __ballot_sync(0xffffffffu, cand);
+            if (cand) {
+                const unsigned at = (head + count + __popc(bal & lt_mask)) & (MN_RING - 1);
+                wval[at] = x[j];
+                wkey[at] = (unsigned)kj | ((unsigned)dj << 12) | (w ? rep1 : rep0);
+            }
+            count += __popc(bal);
+        }
+        __syncwarp();
+        while (count >= 32u) flush32(32u);
+        __syncwarp();
+        e += (long long)NT * V;
+        d += step_d;
+        row += step_r;
+        if (d >= D) { d -= D; ++row; }
+    }
+    if (count) flush32(count);
+    __syncthreads();
+    for (int i = threadIdx.x; i < KD; i += blockDim.x) {
+        const unsigned b = sbelow[i], t = sties[i];
+        if (b) atomicAdd(&ws.below[i], b);
+        if (t) atomicAdd(&ws.above[i], t);
+    }
+}
+
+// one CTA per (type, dim): rank bookkeeping (below / tie plateau / list / above), NaN count and selection inside
+// the list, exact fallback over the type's own rows when the bracket missed or the list overflowed
+template <typename T>
+__global__ void __launch_bounds__(MN_FIN_THREADS)
+mn_finish_kernel(const T *__restrict__ X, long long n, int D, long long ldx, const int *__restrict__ code,
+                 MnWs<T> ws, T *__restrict__ cent, double *__restrict__ cent64)
 {
     using KO = KeyOf<T>;
     using Key = typename KO::type;
     constexpr int BITS = sizeof(Key) * 8;
-    constexpr int STAGE = MS_STAGE_BYTES / (int)sizeof(T);
+    constexpr int STAGE = MN_STAGE_BYTES / (int)sizeof(T);
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    T *s_stage = reinterpret_cast<T *>(smem_raw);
     __shared__ unsigned int hist[512];
     __shared__ long long sh[4];
-    __shared__ unsigned long long s_sum[5];
-    __shared__ unsigned int s_off[MS_MAXITEMS_PER_TYPE + 1];
-    __shared__ T s_stage[STAGE];
-    __shared__ int s_over;
+    __shared__ unsigned long long s_nan, s_valid;
     const int kd = blockIdx.x;
     const int k = kd / D, d = kd - k * D;
-    const int i0 = ws.item_first[k], i1 = ws.item_first[k + 1];
-    const int nit = i1 - i0;
-    if (threadIdx.x < 5) s_sum[threadIdx.x] = 0ULL;
-    if (threadIdx.x == 0) s_over = nit > MS_MAXITEMS_PER_TYPE ? 1 : 0;
-    __syncthreads();
-    {
-        unsigned long long a[2] = {0, 0};
-        for (int q = threadIdx.x; q < nit; q += blockDim.x) {
-            const unsigned int *c = ws.cnt + ((size_t)(i0 + q) * D + d) * 5;
-            a[0] += c[0]; a[1] += c[1];
-            const unsigned nc = c[4];
-            if (nc > ws.capi) s_over = 1;
-            if (q < MS_MAXITEMS_PER_TYPE) s_off[q + 1] = nc < ws.capi ? nc : ws.capi;
-        }
-        // one shared 64-bit atomic per warp (they are CAS loops: 256 contending threads would serialise)
-#pragma unroll
-        for (int j = 0; j < 2; ++j) {
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) a[j] += __shfl_xor_sync(0xffffffffu, a[j], o);
-            if ((threadIdx.x & 31) == 0 && a[j]) atomicAdd(&s_sum[j], a[j]);
-        }
-    }
-    __syncthreads();
+    const long long Nk = (long long)ws.type_cnt[k];
+    const long long below = ws.below[kd], tie_cnt = ws.above[kd];
+    const unsigned cap = ws.cap[k];
+    const int KD = gridDim.x;
+    // the MN_REP replica lists of this (type, dim): counts and their exclusive prefix (one warp)
+    __shared__ unsigned int s_roff[MN_REP + 1];
+    __shared__ int s_over;
     if (threadIdx.x < 32) {
-        // inclusive scan of s_off[1..m] by one warp, 32 entries per step
-        const int m = nit < MS_MAXITEMS_PER_TYPE ? nit : MS_MAXITEMS_PER_TYPE;
-        unsigned carry = 0;
-        for (int base = 0; base < m; base += 32) {
-            const int q = base + threadIdx.x;
-            unsigned v = q < m ? s_off[q + 1] : 0u;
+        static_assert(MN_REP == 32, "one lane per replica");
+        const unsigned raw = ws.ncand[(size_t)threadIdx.x * KD + kd];
+        const unsigned c = raw < cap ? raw : cap;
+        const bool ov = __any_sync(0xffffffffu, raw > cap);
+        unsigned incl = c;
 #pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const unsigned u = __shfl_up_sync(0xffffffffu, v, o);
-                if ((int)threadIdx.x >= o) v += u;
-            }
-            if (q < m) s_off[q + 1] = v + carry;
-            carry += __shfl_sync(0xffffffffu, v, 31);
+        for (int o = 1; o < 32; o <<= 1) {
+            const unsigned v = __shfl_up_sync(0xffffffffu, incl, o);
+            if ((int)threadIdx.x >= o) incl += v;
         }
-        if (threadIdx.x == 0) { s_off[0] = 0; s_sum[4] = carry; }
+        s_roff[threadIdx.x + 1] = incl;
+        if (threadIdx.x == 0) { s_roff[0] = 0u; s_over = ov ? 1 : 0; s_nan = 0ULL; s_valid = 0ULL; }
     }
     __syncthreads();
     const bool overflow = s_over != 0;
-    const long long below = (long long)s_sum[0], above = (long long)s_sum[1], nlist = (long long)s_sum[4];
-    const unsigned toff = ws.type_off[k];
-    const long long Nk = (long long)ws.type_off[k + 1] - toff;
+    const long long nlist = s_roff[MN_REP];
+    const T *cl = ws.cand + ws.cand_off[k] + (size_t)d * cap;  // replica r at + r * D * cap
+    const size_t rstride = (size_t)D * cap;
     const T lo = ws.piv[2 * kd], hi = ws.piv[2 * kd + 1];
-    // the lists hold the closed bracket [lo, hi] and every NaN; with lo == hi the ties were counted
-    // instead of listed: ties = Nk - below - above - listed
-    const long long ties = lo == hi ? Nk - below - above - nlist : 0;
+    const long long ties = lo == hi ? tie_cnt : 0;
     const bool staged = !overflow && nlist <= STAGE;
-    if (staged) {
-        // warp w copies the lists of items w, w + 8, ... (each a short contiguous run)
+    // every list element, NaN included (warp w walks the replicas w, w + 8, ...)
+    auto lst_raw = [&](auto f) {
         const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-        // four lists per round, so that four independent global loads are in flight per lane
-        constexpr int NW = MS_FIN_THREADS / 32;
-        for (int q = warp; q < nit; q += 4 * NW) {
-            const T *cl[4];
-            unsigned o[4], c[4], cmax = 0;
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                const int qq = q + u * NW;
-                const bool ok = qq < nit;
-                cl[u] = ws.cand + ((size_t)(i0 + (ok ? qq : q)) * D + d) * ws.capi;
-                o[u] = ok ? s_off[qq] : 0u;
-                c[u] = ok ? s_off[qq + 1] - o[u] : 0u;
-                cmax = c[u] > cmax ? c[u] : cmax;
-            }
-            for (unsigned i = lane; i < cmax; i += 32) {
-                T v[4];
-#pragma unroll
-                for (int u = 0; u < 4; ++u) v[u] = i < c[u] ? cl[u][i] : (T)0;
-#pragma unroll
-                for (int u = 0; u < 4; ++u)
-                    if (i < c[u]) s_stage[o[u] + i] = v[u];
-            }
+        for (int r = warp; r < MN_REP; r += MN_FIN_THREADS / 32) {
+            const unsigned o = s_roff[r], c = s_roff[r + 1] - o;
+            const T *src = cl + (size_t)r * rstride;
+            for (unsigned i = lane; i < c; i += 32) f(o + i, src[i]);
         }
-        __syncthreads();
-    }
-    // every list element, NaN included
+    };
+    if (staged) lst_raw([&](unsigned at, T x) { s_stage[at] = x; });
+    __syncthreads();
     auto lst_all = [&](auto f) {
         if (staged) {
-            for (unsigned i = threadIdx.x; i < (unsigned)nlist; i += blockDim.x) f(s_stage[i]);
+            for (long long i = threadIdx.x; i < nlist; i += blockDim.x) f(s_stage[i]);
         } else {
-            for (int q = 0; q < nit; ++q) {
-                const T *cl = ws.cand + ((size_t)(i0 + q) * D + d) * ws.capi;
-                const unsigned c = s_off[q + 1] - s_off[q];
-                for (unsigned i = threadIdx.x; i < c; i += blockDim.x) f(cl[i]);
-            }
+            lst_raw([&](unsigned, T x) { f(x); });
         }
     };
     long long n_nan = 0;
     if (!overflow) {
         unsigned my = 0;
         lst_all([&](T x) { my += x != x ? 1u : 0u; });
-        if (my) atomicAdd(&s_sum[3], (unsigned long long)my);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) my += __shfl_xor_sync(0xffffffffu, my, o);
+        if ((threadIdx.x & 31) == 0 && my) atomicAdd(&s_nan, (unsigned long long)my);
         __syncthreads();
-        n_nan = (long long)s_sum[3];
+        n_nan = (long long)s_nan;
     }
     const long long nmid = nlist - n_nan;  // listed, orderable
     const long long nvalid = Nk - n_nan;
@@ -695,8 +779,8 @@ msort_finish_kernel(const T *__restrict__ X, int D, long long ldx, MsWs<T> ws, T
     if (nvalid <= 0 && !overflow) {
         med = (T)NAN;
     } else {
-        const long long r0 = (nvalid - 1) / 2, r1 = nvalid / 2;
-        // where does each rank land?  0: < lo (fail) 1: the tie plateau lo == hi 2: the lists 4: beyond (fail)
+        const long long q0 = (nvalid - 1) / 2, q1 = nvalid / 2;
+        // where does each rank land?  0: < lo (fail) 1: the tie plateau lo == hi 2: the list 4: beyond (fail)
         auto region = [&](long long r, long long &rin) -> int {
             if (r < below) return 0;
             r -= below;
@@ -706,21 +790,21 @@ msort_finish_kernel(const T *__restrict__ X, int D, long long ldx, MsWs<T> ws, T
             return 4;
         };
         long long j0 = 0, j1 = 0;
-        const int g0 = overflow ? 0 : region(r0, j0), g1 = overflow ? 0 : region(r1, j1);
+        const int g0 = overflow ? 0 : region(q0, j0), g1 = overflow ? 0 : region(q1, j1);
         T v0, v1;
         if (overflow || g0 == 0 || g0 == 4 || g1 == 0 || g1 == 4) {
-            // exact fallback: radix select over this type's own rows
+            // exact fallback: radix select over this type's own rows (found by scanning the codes)
             if (threadIdx.x == 0) atomicAdd(&ws.hdr->fail, 1u);
-            __shared__ unsigned long long s_valid;
-            if (threadIdx.x == 0) s_valid = 0ULL;
-            __syncthreads();
             {
                 unsigned long long my = 0;
-                for (long long i = threadIdx.x; i < Nk; i += blockDim.x) {
-                    const T x = X[(long long)ws.sorted_rows[toff + i] * ldx + d];
-                    my += x == x ? 1ULL : 0ULL;
-                }
-                if (my) atomicAdd(&s_valid, my);
+                for (long long i = threadIdx.x; i < n; i += blockDim.x)
+                    if (__ldg(code + i) == k) {
+                        const T x = X[i * ldx + d];
+                        my += x == x ? 1ULL : 0ULL;
+                    }
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) my += __shfl_xor_sync(0xffffffffu, my, o);
+                if ((threadIdx.x & 31) == 0 && my) atomicAdd(&s_valid, my);
             }
             __syncthreads();
             const long long nv = (long long)s_valid;
@@ -728,10 +812,11 @@ msort_finish_kernel(const T *__restrict__ X, int D, long long ldx, MsWs<T> ws, T
                 v0 = v1 = (T)NAN;
             } else {
                 auto col = [&](auto f) {
-                    for (long long i = threadIdx.x; i < Nk; i += blockDim.x) {
-                        const T x = X[(long long)ws.sorted_rows[toff + i] * ldx + d];
-                        if (x == x) f(x);
-                    }
+                    for (long long i = threadIdx.x; i < n; i += blockDim.x)
+                        if (__ldg(code + i) == k) {
+                            const T x = X[i * ldx + d];
+                            if (x == x) f(x);
+                        }
                 };
                 cta_select2_raw<T>(col, (nv - 1) / 2, nv / 2, hist, sh, (Key)0, BITS - 8, v0, v1);
             }
@@ -765,65 +850,52 @@ msort_finish_kernel(const T *__restrict__ X, int D, long long ldx, MsWs<T> ws, T
 
 static size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
 
-struct MsPlan {
-    unsigned item_rows, capi, ni_max;
-    int TR;
-};
-
-static MsPlan ms_plan(long long n, int K, int D, size_t elt)
+static size_t mn_stream_smem(int K, int D, size_t elt)
 {
-    MsPlan p;
-    long long ir = (n + (long long)sm_count() * 16 - 1) / ((long long)sm_count() * 16);
-    ir = (ir + 31) / 32 * 32;
-    if (ir < 128) ir = 128;
-    p.item_rows = (unsigned)ir;
-    p.capi = (unsigned)(0.35 * (double)ir) + 32;
-    p.ni_max = (unsigned)(n / ir) + (unsigned)K + 2;
-    long long tr = (48 * 1024) / ((long long)MS_PROC * 2 * D * (long long)elt);  // ~48 KB of tiles per CTA
-    if (tr > 32) tr = 32;
-    p.TR = (int)(tr < 4 ? 4 : tr);
-    return p;
+    const size_t kd = (size_t)K * D;
+    return 2 * kd * elt + (size_t)K * 8 + 2 * kd * 4 + (size_t)K * 4;
 }
 
 template <typename T>
-static size_t ms_ws_bytes(long long n, int K, int D)
+static size_t mn_ws_bytes(long long n, int K, int D)
 {
-    const MsPlan p = ms_plan(n, K, D, sizeof(T));
     const size_t kd = (size_t)K * D;
     size_t b = 256;                                   // header
-    b += align256((size_t)K * 4);                     // cursor
     b += align256((size_t)K * 8);                     // type_cnt
-    b += align256((size_t)(K + 1) * 4) * 2;           // type_off, item_first
-    b += align256((size_t)p.ni_max * 4) * 3;          // item_k, item_r0, item_r1
-    b += align256((size_t)n * 4);                     // sorted_rows
+    b += align256((size_t)K * 4);                     // samp_cur
+    b += align256(kd * 4) * 2;                        // below, above
+    b += align256(kd * 4 * MN_REP);                   // ncand
+    b += align256((size_t)K * 8);                     // cand_off
+    b += align256((size_t)K * 4) * 3;                 // cap, sstride, scap
+    b += align256((size_t)K * 8);                     // samp_off
     b += align256(kd * 2 * sizeof(T));                // piv
-    b += align256((size_t)p.ni_max * D * 5 * 4);      // cnt
-    b += align256((size_t)p.ni_max * D * p.capi * sizeof(T));  // cand
+    b += align256(((size_t)(n / 16) * 5 / 4 + (size_t)K * (MN_SAMPLE_MIN * 5 / 4 + 64 + 64)) * D * sizeof(T));  // samp
+    b += align256((size_t)(0.35 * (double)n * D) * sizeof(T) + (size_t)65 * MN_REP * kd * sizeof(T) + 4096);  // cand pool
     return b;
 }
 
 template <typename T>
-static int median_run_sorted(const T *X, long long n, int D, long long ldx, const int *code, int K, T *cent,
+static int median_run_stream(const T *X, long long n, int D, long long ldx, const int *code, int K, T *cent,
                              double *cent64, void *workspace, cudaStream_t st)
 {
-    const MsPlan pl = ms_plan(n, K, D, sizeof(T));
     const size_t kd = (size_t)K * D;
-    MsWs<T> ws;
+    MnWs<T> ws;
     unsigned char *p = (unsigned char *)workspace;
-    ws.hdr = (MsHeader *)p; p += 256;
-    ws.cursor = (unsigned int *)p; p += align256((size_t)K * 4);
+    ws.hdr = (MnHeader *)p; p += 256;
     ws.type_cnt = (unsigned long long *)p; p += align256((size_t)K * 8);
+    ws.samp_cur = (unsigned int *)p; p += align256((size_t)K * 4);
+    ws.below = (unsigned int *)p; p += align256(kd * 4);
+    ws.above = (unsigned int *)p; p += align256(kd * 4);
+    ws.ncand = (unsigned int *)p; p += align256(kd * 4 * MN_REP);
     const size_t zero_bytes = (size_t)(p - (unsigned char *)workspace);
-    ws.type_off = (unsigned int *)p; p += align256((size_t)(K + 1) * 4);
-    ws.item_first = (int *)p; p += align256((size_t)(K + 1) * 4);
-    ws.item_k = (int *)p; p += align256((size_t)pl.ni_max * 4);
-    ws.item_r0 = (unsigned int *)p; p += align256((size_t)pl.ni_max * 4);
-    ws.item_r1 = (unsigned int *)p; p += align256((size_t)pl.ni_max * 4);
-    ws.sorted_rows = (unsigned int *)p; p += align256((size_t)n * 4);
+    ws.cand_off = (unsigned long long *)p; p += align256((size_t)K * 8);
+    ws.cap = (unsigned int *)p; p += align256((size_t)K * 4);
+    ws.sstride = (unsigned int *)p; p += align256((size_t)K * 4);
+    ws.scap = (unsigned int *)p; p += align256((size_t)K * 4);
+    ws.samp_off = (unsigned long long *)p; p += align256((size_t)K * 8);
     ws.piv = (T *)p; p += align256(kd * 2 * sizeof(T));
-    ws.cnt = (unsigned int *)p; p += align256((size_t)pl.ni_max * D * 5 * 4);
+    ws.samp = (T *)p; p += align256(((size_t)(n / 16) * 5 / 4 + (size_t)K * (MN_SAMPLE_MIN * 5 / 4 + 64 + 64)) * D * sizeof(T));
     ws.cand = (T *)p;
-    ws.item_rows = pl.item_rows; ws.capi = pl.capi; ws.ni_max = pl.ni_max;
     PILOT_CUDA(cudaMemsetAsync(workspace, 0, zero_bytes, st));
     long long blocks = (n + 2047) / 2048;
     const long long cap = (long long)sm_count() * 8;
@@ -831,51 +903,58 @@ static int median_run_sorted(const T *X, long long n, int D, long long ldx, cons
     if (blocks < 1) blocks = 1;
     msort_count_kernel<<<(unsigned)blocks, 256, K * sizeof(unsigned int), st>>>(code, n, K, ws.type_cnt);
     PILOT_LAUNCH_CHECK();
-    msort_plan_kernel<T><<<1, 256, 0, st>>>(K, ws);
-    PILOT_LAUNCH_CHECK();
-    msort_scatter_kernel<T><<<(unsigned)blocks, 256, 2 * K * sizeof(unsigned int), st>>>(code, n, K, ws);
-    PILOT_LAUNCH_CHECK();
-    msort_pivot_kernel<T><<<(unsigned)kd, 256, 0, st>>>(X, D, ldx, ws);
+    mn_plan_kernel<T><<<1, 32, 0, st>>>(K, D, ws);
     PILOT_LAUNCH_CHECK();
     {
-        const size_t smem = (size_t)MS_PROC * 2 * pl.TR * D * sizeof(T);
-        // widest cp.async every row start and row length allow (the tile rows inherit the alignment)
-        const size_t rowb = (size_t)D * sizeof(T), strideb = (size_t)ldx * sizeof(T);
-        int vb = (int)sizeof(T);
-        if (rowb % 16 == 0 && strideb % 16 == 0 && ((uintptr_t)X % 16) == 0) vb = 16;
-        else if (rowb % 8 == 0 && strideb % 8 == 0 && ((uintptr_t)X % 8) == 0) vb = 8;
-#define MS_LAUNCH(VBV)                                                                                          \
-        do {                                                                                                    \
-            PILOT_CUDA(cudaFuncSetAttribute(msort_stream_kernel<T, VBV>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
-                                            (int)smem));                                                        \
-            int per_sm = 1;                                                                                     \
-            PILOT_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, msort_stream_kernel<T, VBV>,      \
-                                                                     MS_PROC * 64, smem));                      \
-            if (per_sm < 1) per_sm = 1;                                                                         \
-            if (per_sm > 4) per_sm = 4;                                                                         \
-            msort_stream_kernel<T, VBV><<<sm_count() * per_sm, MS_PROC * 64, smem, st>>>(X, D, ldx, pl.TR, ws);  \
-        } while (0)
-        if (vb == 16) MS_LAUNCH(16);
-        else if (vb == 8) MS_LAUNCH(8);
-        else MS_LAUNCH((int)sizeof(T));
-#undef MS_LAUNCH
+        long long sblocks = (n + 1023) / 1024;  // one global atomic per (CTA, type): ~20 ns each, serialised per type
+        if (sblocks > 4LL * sm_count()) sblocks = 4LL * sm_count();
+        mn_sample_kernel<T><<<(unsigned)sblocks, 256, 2 * K * sizeof(unsigned int), st>>>(X, n, D, ldx, code, K, ws);
+    }
+    PILOT_LAUNCH_CHECK();
+    PILOT_CUDA(cudaFuncSetAttribute(mn_pivot_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    (int)(MN_MCAP * sizeof(T))));
+    mn_pivot_kernel<T><<<(unsigned)kd, 256, MN_MCAP * sizeof(T), st>>>(D, ws);
+    PILOT_LAUNCH_CHECK();
+    {
+        // fast path: contiguous rows, 16-byte aligned, a 128-bit vector spans at most two rows
+        const bool vec = ldx == D && ((uintptr_t)X % 16) == 0 && D >= 16 / (int)sizeof(T) && K <= 4096 && D <= 4096;
+        const size_t ring = vec ? (size_t)(MN_THREADS / 32) * MN_RING * (sizeof(T) + 4) + 8 : 0;
+        const size_t smem = mn_stream_smem(K, D, sizeof(T)) + ring;
+        int per_sm = 1;
+        if (vec) {
+            PILOT_CUDA(cudaFuncSetAttribute(mn_stream_vec_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            PILOT_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, mn_stream_vec_kernel<T>, MN_THREADS, smem));
+        } else {
+            PILOT_CUDA(cudaFuncSetAttribute(mn_stream_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            PILOT_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, mn_stream_kernel<T>, MN_THREADS, smem));
+        }
+        if (per_sm < 1) per_sm = 1;
+        if (per_sm > 4) per_sm = 4;
+        long long ctas = (long long)sm_count() * per_sm;
+        const long long need = (n * D + (long long)MN_THREADS * 16 - 1) / ((long long)MN_THREADS * 16);
+        if (ctas > need) ctas = need;
+        if (ctas < 1) ctas = 1;
+        if (vec) mn_stream_vec_kernel<T><<<(unsigned)ctas, MN_THREADS, smem, st>>>(X, n, D, code, K, ws);
+        else     mn_stream_kernel<T><<<(unsigned)ctas, MN_THREADS, smem, st>>>(X, n, D, ldx, code, K, ws);
         PILOT_LAUNCH_CHECK();
     }
-    msort_finish_kernel<T><<<(unsigned)kd, MS_FIN_THREADS, 0, st>>>(X, D, ldx, ws, cent, cent64);
+    PILOT_CUDA(cudaFuncSetAttribute(mn_finish_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, MN_STAGE_BYTES));
+    mn_finish_kernel<T><<<(unsigned)kd, MN_FIN_THREADS, MN_STAGE_BYTES, st>>>(X, n, D, ldx, code, ws, cent, cent64);
     PILOT_LAUNCH_CHECK();
     return 0;
 }
 
 static bool median_use_sorted(long long n, int K, int D)
 {
-    return n >= 65536 && n < (1LL << 32) && D <= 64 * MS_MAXCH && K <= 4096;
+    return n >= 65536 && n < (1LL << 32) && K <= 4096 &&
+           mn_stream_smem(K, D, 8) + (size_t)(MN_THREADS / 32) * MN_RING * 12 + 8 <= MN_SMEM_MAX;
 }
 
 size_t median_ws_bytes(long long n, int K, int D)
 {
     size_t a = median_ws_bytes_impl(K, D);
     if (median_use_sorted(n, K, D)) {
-        const size_t b = ms_ws_bytes<double>(n, K, D);
+        const size_t b = mn_ws_bytes<double>(n, K, D);
         if (b > a) a = b;
     }
     return a;
@@ -898,9 +977,9 @@ extern "C" int pilot_centroid_median(const void *X, int dtype, int64_t n_cells, 
     cudaStream_t st = (cudaStream_t)stream;
     if (median_use_sorted(n_cells, K, D)) {
         if (dtype == PILOT_F32)
-            return median_run_sorted<float>((const float *)X, n_cells, D, ldx, ct_code, K, (float *)centroids,
+            return median_run_stream<float>((const float *)X, n_cells, D, ldx, ct_code, K, (float *)centroids,
                                             centroids_f64, workspace, st);
-        return median_run_sorted<double>((const double *)X, n_cells, D, ldx, ct_code, K, (double *)centroids,
+        return median_run_stream<double>((const double *)X, n_cells, D, ldx, ct_code, K, (double *)centroids,
                                          centroids_f64, workspace, st);
     }
     if (dtype == PILOT_F32)

@@ -85,10 +85,19 @@ def test_centroid_median_streaming_path(dtype, case):
         code = np.minimum((rng.exponential(1.2, size=n)).astype(np.int32), K - 1)  # one dominant, some rare
         code[:K] = np.arange(K)
     elif case == "adversarial_sample":
-        # every column sorted along the rows: the work items (contiguous row blocks of a type) around
-        # the median then lie ENTIRELY inside the pivot bracket, their candidate lists overflow and the
-        # pairs must take the exact fallback
-        X = np.sort(X, axis=0)
+        # the rows the kernel samples (hash(row) % stride == 0, mn_hash / mn_plan_kernel in median.cu) carry
+        # values far above the rest: every pivot bracket misses the true median and the pairs must take the
+        # exact in-kernel fallback.  Columns 40.. are additionally sorted along the rows (harmless here; it
+        # was the adversarial input of the round-1 design).
+        i = np.arange(n, dtype=np.uint64)
+        h = (i * np.uint64(0x9E3779B1)) & np.uint64(0xffffffff)
+        h ^= h >> np.uint64(15)
+        h = (h * np.uint64(0x85EBCA77)) & np.uint64(0xffffffff)
+        h ^= h >> np.uint64(13)
+        stride = np.array([max(1, -(-int((code == k).sum()) // 2048)) for k in range(K)], dtype=np.uint64)
+        sampled = (h % stride[code]) == 0
+        X[:, 40:] = np.sort(X[:, 40:], axis=0)
+        X[sampled, :40] += 50.0
     cent, cent64 = ops.centroid_median(dev(X), dev(code), K)
     fallbacks = ops.median_fallbacks(K, D)
     if case == "adversarial_sample":
