@@ -538,7 +538,7 @@ class DeviceStep:
         annot = obs[["cell_types", "sampleID", "status"]].copy()
         annot.columns = ["cell_type", "sampleID", "status"]
         self.lab = tl._Labels(annot, "cell_type", "sampleID")      # codes on device + perms
-        self.X = tl._embedding_to_device(X)
+        self.X = tl._embedding_ready(tl._embedding_to_device(X))
 
     def run(self, timers=None):
         from pilot_b200 import ops, pairs

@@ -70,7 +70,8 @@ template <int KP, bool SYM>
 __global__ void __launch_bounds__(SKT_WARPS * 32, 1)
 sinkhorn_tail_kernel(const double *__restrict__ props, int K, SkParams prm, PairMap pm,
                      const double *__restrict__ gK0, const double *__restrict__ gK0T,
-                     const double *__restrict__ gMK, const int *__restrict__ asym_flag,
+                     const double *__restrict__ gMK, const double *__restrict__ gc0,
+                     const int *__restrict__ asym_flag,
                      const double *__restrict__ scratch, SkTail tail,
                      unsigned long long *__restrict__ tail_counter, double *__restrict__ out,
                      int *__restrict__ iters_out, int *__restrict__ abs_out, int *__restrict__ status_out,
@@ -137,6 +138,12 @@ sinkhorn_tail_kernel(const double *__restrict__ props, int K, SkParams prm, Pair
             __syncwarp();
             double T[R];
             skt_matvec<KP, R>(sK0, row[0], ub, T);
+            if (ii == 0) {
+                // a slot can be handed over right after it was refilled: the panels take the first product
+                // K0^T (1/K) from the setup kernel's c0 (summed in another order), and so must we
+#pragma unroll
+                for (int rr = 0; rr < R; ++rr) T[rr] = __ldg(gc0 + row[rr]);
+            }
             if (ctl) {
                 if (ctl & SKT_BAD) { status = -1; break; }
                 bool conv = false;
@@ -246,10 +253,10 @@ static int skt_launch_t(const double *props, int K, const SkParams &prm, const P
     const size_t smem = sizeof(double) * ((size_t)(SYM ? 2 : 3) * KP * KP + (size_t)SKT_WARPS * 3 * KP);
     PILOT_CUDA(cudaFuncSetAttribute(sinkhorn_tail_kernel<KP, SYM>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                     (int)smem));
-    const double *K0 = setup, *K0T = K0 + KP * KP, *MK = K0T + KP * KP;
+    const double *K0 = setup, *K0T = K0 + KP * KP, *MK = K0T + KP * KP, *c0 = MK + KP * KP;
     const int *asym = reinterpret_cast<const int *>(setup + 3 * KP * KP + KP);
     sinkhorn_tail_kernel<KP, SYM><<<sm_count(), SKT_WARPS * 32, smem, st>>>(
-        props, K, prm, pm, K0, K0T, MK, asym, scratch, tail, tail_counter, out, iters, absn, status, redo, n_redo);
+        props, K, prm, pm, K0, K0T, MK, c0, asym, scratch, tail, tail_counter, out, iters, absn, status, redo, n_redo);
     PILOT_LAUNCH_CHECK();
     return 0;
 }

@@ -180,11 +180,21 @@ class _Labels:
                                   bool(normalization == True))  # noqa: E712  (reference: `normalization == True`)
 
 
-def _embedding_to_device(data) -> torch.Tensor:
+def _shard_min_bytes() -> int:
+    return int(os.environ.get("PILOT_SHARD_H2D_MIN_BYTES", str(32 << 20)))
+
+
+def _embedding_to_device(data, group=None) -> torch.Tensor:
     """Stage the embedding.  Page-locked input (e.g. a torch pinned tensor's numpy view) is copied on a
     side stream so that the label factorisation, the histogram and the proportion table -- host work
     plus small kernels -- run while the 200 MB cross PCIe; the compute stream waits for the copy before
-    it is first read (stage 2).  Pageable input is a plain blocking copy."""
+    it is first read (stage 2).  Pageable input is a plain blocking copy.
+
+    Several ranks (torch.distributed initialised; every rank holds the same host array, as in any SPMD
+    launch of the same script): rank r uploads only rows [r n/N, (r+1) n/N) over ITS PCIe link and the
+    slices are exchanged with one in-place NCCL all-gather over NVLink right before stage 2 -- the host
+    memory system no longer serves N full copies at once (round 1: the 8-rank end-to-end step took 2x
+    the 1-rank one for this reason)."""
     X = data.to_numpy() if isinstance(data, pd.DataFrame) else np.asarray(data)
     if X.dtype not in (np.float32, np.float64):
         X = X.astype(np.float64)  # pandas' nanmedian promotes non-float input to float64
@@ -193,19 +203,40 @@ def _embedding_to_device(data) -> torch.Tensor:
     if not X.flags.c_contiguous:
         X = np.ascontiguousarray(X)
     host = torch.from_numpy(X)
-    if not host.is_pinned():
-        return _to_device(X)
     dev = _device()
+    nranks, rank = pairs.world(group)
+    n = X.shape[0]
+    if nranks > 1 and X.nbytes >= _shard_min_bytes():
+        per = -(-n // nranks)
+        full = torch.empty((per * nranks, X.shape[1]), dtype=host.dtype, device=dev)
+        r0, r1 = min(n, rank * per), min(n, (rank + 1) * per)
+        src, dst = host[r0:r1], full[r0:r1]
+        gather = (per, rank, group)
+    else:
+        full = None
+        src, dst, gather = host, None, None
+    if not host.is_pinned():
+        if gather is None:
+            return _to_device(X)
+        dst.copy_(src)  # blocking, pageable
+        X_dev = full[:n]
+        X_dev._pilot_gather = (full,) + gather
+        return X_dev
     main = torch.cuda.current_stream(dev)
     side = _copy_stream(dev)
-    X_dev = torch.empty(host.shape, dtype=host.dtype, device=dev)  # allocated in compute-stream order
+    if gather is None:
+        full = torch.empty(host.shape, dtype=host.dtype, device=dev)  # allocated in compute-stream order
+        dst = full
     side.wait_stream(main)
     with torch.cuda.stream(side):
-        X_dev.copy_(host, non_blocking=True)
-    X_dev.record_stream(side)  # the allocator must not hand the block out again while the copy is in flight
+        dst.copy_(src, non_blocking=True)
+    full.record_stream(side)  # the allocator must not hand the block out again while the copy is in flight
     done = torch.cuda.Event()
     done.record(side)
+    X_dev = full[:n]
     X_dev._pilot_ready = done  # consumed by _cost_device
+    if gather is not None:
+        X_dev._pilot_gather = (full,) + gather
     return X_dev
 
 
@@ -278,10 +309,25 @@ def Cluster_Representations(df, cell_col=0, sample_col=1, regulizer=0.2, normali
 # ---------------------------------------------------------------------------
 # Stage 2: cost matrix (Trajectory.py:441-475)
 # ---------------------------------------------------------------------------
-def _cost_device(lab: _Labels, X_dev: torch.Tensor, metric) -> Tuple[torch.Tensor, torch.Tensor]:
+def _embedding_ready(X_dev: torch.Tensor) -> torch.Tensor:
+    """Make the compute stream wait for the staged embedding (side-stream copy, rank slices)."""
     ready = getattr(X_dev, "_pilot_ready", None)
     if ready is not None:
         torch.cuda.current_stream(X_dev.device).wait_event(ready)
+        X_dev._pilot_ready = None
+    gather = getattr(X_dev, "_pilot_gather", None)
+    if gather is not None:
+        # every rank uploaded its row slice: exchange them over NVLink (in place: rank r's slice is already
+        # where the all-gather would put it)
+        import torch.distributed as dist
+        full, per, rank, group = gather
+        dist.all_gather_into_tensor(full.view(-1), full[rank * per:(rank + 1) * per].reshape(-1), group=group)
+        X_dev._pilot_gather = None
+    return X_dev
+
+
+def _cost_device(lab: _Labels, X_dev: torch.Tensor, metric) -> Tuple[torch.Tensor, torch.Tensor]:
+    _embedding_ready(X_dev)
     if X_dev.shape[0] != lab.n:
         raise ValueError(f"Item wrong length {lab.n} instead of {X_dev.shape[0]}.")
     _, cent64_raw = ops.centroid_median(X_dev, lab.ct_dev, lab.K_raw)
@@ -315,9 +361,11 @@ def _check_emd_inputs(P: np.ndarray, cost: np.ndarray) -> None:
                              "a and b vector must have the same sum")
 
 
-def wasserstein_d(Clu_rep, cost, regularized="unreg", reg=0.1):
+def wasserstein_d(Clu_rep, cost, regularized="unreg", reg=0.1, precision="f64"):
     """All ordered sample pairs: exact EMD (``regularized == "unreg"``) or stabilised
-    Sinkhorn (anything else).  Returns ``(EMD ndarray [S,S], DataFrame indexed by sampleID)``."""
+    Sinkhorn (anything else).  Returns ``(EMD ndarray [S,S], DataFrame indexed by sampleID)``.
+    ``precision`` is an extension of the reference signature: "f64" (default, within 1e-9 of POT) or
+    "f32" (single-precision solvers, within 1e-4)."""
     samples_id = list(Clu_rep.keys())
     P = np.ascontiguousarray(np.stack([np.asarray(Clu_rep[s], dtype=np.float64) for s in samples_id])) \
         if samples_id else np.zeros((0, 0))
@@ -330,7 +378,7 @@ def wasserstein_d(Clu_rep, cost, regularized="unreg", reg=0.1):
         _check_emd_inputs(P, C)
         sym = pairs.cost_is_symmetric_metric_like(C)  # K x K on the host: no device round trip
     EMD, EMD_T = pairs.all_pairs_host(_to_device(P), _to_device(C), regularized, reg, symmetric=sym,
-                                      with_transpose=True)
+                                      with_transpose=True, precision=precision)
     return EMD, _emd_frame(EMD, samples_id, EMD_T)
 
 
@@ -350,7 +398,7 @@ def return_real_labels(df, category="status", sample_col=1):
 def wasserstein_distance(adata, emb_matrix="X_PCA", clusters_col="cell_types", sample_col="sampleID",
                          status="status", metric="cosine", regulizer=0.2, normalization=True,
                          regularized="unreg", reg=0.1, res=0.01, steper=0.01, data_type="scRNA",
-                         return_sil_ari=False):
+                         return_sil_ari=False, precision="f64"):
     """Drop-in for ``pilotpy.tl.wasserstein_distance``: writes ``data``, ``annot``,
     ``proportions``, ``cost``, ``EMD_df``, ``EMD`` and ``real_labels`` into ``adata.uns``."""
     if return_sil_ari:
@@ -382,9 +430,9 @@ def wasserstein_distance(adata, emb_matrix="X_PCA", clusters_col="cell_types", s
             raise ValueError("label codes out of range")
         if regularized == "unreg":
             _check_emd_inputs(props_h, np.empty((lab.K, lab.K)))
-        EMD, EMD_T = pairs.all_pairs_host(props, cost_norm, regularized, reg, with_transpose=True)
+        EMD, EMD_T = pairs.all_pairs_host(props, cost_norm, regularized, reg, with_transpose=True, precision=precision)
     else:
-        emd_dev = pairs.all_pairs(props, cost_norm, regularized, reg)
+        emd_dev = pairs.all_pairs(props, cost_norm, regularized, reg, precision=precision)
         props_h = props.cpu().numpy()
         if int(counts.sum().item()) != lab.n:
             raise ValueError("label codes out of range")

@@ -271,7 +271,8 @@ def test_properties_at_scale():
         assert abs(sk1[i, j] - w) <= SK_RTOL * w
 
 
-@pytest.mark.parametrize("K,reg,S", [(64, 0.1, 100), (64, 0.01, 40), (40, 0.05, 60), (12, 0.1, 460), (48, 0.02, 40)])
+@pytest.mark.parametrize("K,reg,S", [(64, 0.1, 100), (64, 0.01, 40), (40, 0.05, 60), (12, 0.1, 460), (48, 0.02, 40),
+                                     (64, 0.1, 257)])  # 257: slots refilled and handed over at once (first product = c0)
 def test_sinkhorn_bit_reproducible_with_tail_handover(K, reg, S):
     """Small batches end with most problems handed from the DMMA panels to the warp-form tail kernel at
     timing-dependent moments; the results must not depend on it: repeated runs, the panel-only solver of a
