@@ -142,3 +142,30 @@ def test_precomputed_distance_writes_the_uns_contract(tmp_path, monkeypatch):
     assert adata.uns["EMD"] is D and adata.uns["cost"] is cost and adata.uns["proportions"] is feats
     assert list(adata.uns["annot"].columns) == ["cell_type", "sampleID", "status"]
     assert len(adata.uns["real_labels"]) == 5 and len(adata.uns["data"]) == 500
+
+
+def test_object_column_factorize_fast_path_equals_pandas():
+    """The pointer-first factorisation of object label columns returns exactly pd.factorize(sort=False)."""
+    import pandas as pd
+    from pilot_b200 import tl
+    rng = np.random.default_rng(0)
+    n = 120_000
+    names = np.array([f"type{k}" for k in range(17)], dtype=object)
+    shared = pd.Series(names[rng.integers(0, 17, n)], dtype=object)                                  # 17 shared objects
+    dup = pd.Series(np.array([f"s{v}" for v in rng.integers(0, 40, n)], dtype=object), dtype=object)  # every cell its own object
+    mixed = shared.copy()
+    mixed.iloc[::40] = [f"type{k}" for k in rng.integers(0, 17, len(mixed.iloc[::40]))]   # equal values, other objects
+    ints = pd.Series(rng.integers(0, 9, n).astype(object), dtype=object)
+    for col in (shared, mixed, ints):
+        got = tl._factorize_object_column(col)
+        assert got is not None
+        want_codes, want_labels = pd.factorize(col, sort=False)
+        assert np.array_equal(got[0], want_codes) and list(got[1]) == list(want_labels)
+    assert tl._factorize_object_column(dup) is None            # no gain: falls back to pd.factorize
+    withnan = shared.copy()
+    withnan.iloc[5] = np.nan
+    got = tl._factorize_object_column(withnan)
+    want_codes, want_labels = pd.factorize(withnan, sort=False)
+    assert np.array_equal(got[0], want_codes) and list(got[1]) == list(want_labels) and got[0][5] == -1
+    codes, labels = tl._raw_codes(shared.rename("cell_type"))
+    assert codes.dtype == np.int32 and list(labels) == list(pd.factorize(shared, sort=False)[1])
