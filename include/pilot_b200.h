@@ -185,6 +185,18 @@ int pilot_unpack_pairs(const double *packed, int64_t chunk_stride, int S,
                        double *dense, void *stream);
 
 /*
+ * (f-1) Row k-nearest neighbours on the dense S x S distance matrix, the first step of the consumer
+ * pilotpy.pl.trajectory (ploting.py:95-110: pydiffmap DiffusionMap.from_sklearn(k=64) ->
+ * sklearn NearestNeighbors(n_neighbors=k).kneighbors_graph(X, mode='distance'), the rows of X = EMD/EMD.max()
+ * as S-dimensional points, Euclidean metric, the query point itself included).
+ * gram = X X^T (S x S row-major; a plain library GEMM on the caller's side).  Outputs, per row, the k
+ * nearest rows sorted by (distance, index): idx[S*k] (int32) and dist[S*k] (Euclidean, double).
+ * workspace: at least S doubles.  1 <= k <= min(S, 1024).
+ */
+int pilot_knn_rows(const double *gram, int S, int k, int32_t *idx, double *dist,
+                   void *workspace, size_t workspace_bytes, void *stream);
+
+/*
  * Pipe-peak microbenchmarks used as roofline denominators:
  * kind 0 = FP64 FMA, 1 = FP32 FMA, 2 = FP64 mma.sync (DMMA m8n8k4).
  * Runs on `stream`, returns achieved TFLOP/s in *h_tflops (host pointer).

@@ -39,7 +39,7 @@ WS_MEDIAN, WS_SINKHORN, WS_EMD = 0, 1, 2
 EXPORTS = (
     "pilot_abi_version", "pilot_last_error", "pilot_range_count", "pilot_workspace_bytes", "pilot_launch_count",
     "pilot_hist", "pilot_props_finalize", "pilot_centroid_median", "pilot_cdist",
-    "pilot_sinkhorn_pairs", "pilot_emd_pairs", "pilot_unpack_pairs", "pilot_pipe_peak",
+    "pilot_sinkhorn_pairs", "pilot_emd_pairs", "pilot_unpack_pairs", "pilot_knn_rows", "pilot_pipe_peak",
 )
 
 
@@ -94,6 +94,8 @@ def lib():
     L.pilot_emd_pairs.argtypes = [vp, i32, i32, vp, i64, prp, i32, vp, vp, vp, vp, sz, vp]
     L.pilot_unpack_pairs.restype = i32
     L.pilot_unpack_pairs.argtypes = [vp, i64, i32, prp, dbl, vp, vp]
+    L.pilot_knn_rows.restype = i32
+    L.pilot_knn_rows.argtypes = [vp, i32, i32, vp, vp, vp, sz, vp]
     L.pilot_pipe_peak.restype = i32
     L.pilot_pipe_peak.argtypes = [i32, ctypes.POINTER(ctypes.c_double), vp]
     if L.pilot_abi_version() != ABI_VERSION:

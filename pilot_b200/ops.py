@@ -205,6 +205,22 @@ def unpack_pairs(packed: torch.Tensor, chunk_stride: int, S: int, rng: PairRange
     return dense
 
 
+def knn_rows(X: torch.Tensor, k: int) -> Tuple[torch.Tensor, torch.Tensor]:
+    """k nearest rows of every row of X (S x S float64, rows = points), Euclidean, self included, sorted by
+    (distance, index): (idx int32 [S,k], dist float64 [S,k]).  The Gram matrix is a library GEMM (cuBLAS DGEMM
+    through torch.mm); selection and distances run in pilot_knn_rows."""
+    _require_cuda(X)
+    assert X.dim() == 2 and X.dtype == torch.float64
+    S = X.shape[0]
+    gram = torch.mm(X, X.t())
+    idx = torch.empty((S, k), dtype=torch.int32, device=X.device)
+    dist = torch.empty((S, k), dtype=torch.float64, device=X.device)
+    ws = _workspace(max(S * 8, 256), X.device)
+    check(lib().pilot_knn_rows(_ptr(gram), S, int(k), _ptr(idx), _ptr(dist), _ptr(ws), ws.numel(), _stream()),
+          "pilot_knn_rows")
+    return idx, dist
+
+
 def pipe_peak(kind: int) -> float:
     """Measured FP64-FMA (0), FP32-FMA (1) or FP64-mma.sync (2) throughput in TFLOP/s."""
     _require_cuda()
