@@ -16,7 +16,8 @@
  *   - strongly-feasible leaving rule (strict '<' on the first path, '<=' on the second)
  *   - objective accumulated as sum(flow * M) over real arcs
  * Parity is UNPINNED against POT itself (POT cannot be installed here); the
- * optimum is cross-checked against SciPy HiGHS in tests/test_oracle_emd.py.
+ * optimum is cross-checked against SciPy HiGHS in tests/test_oracle_ot.py and, wherever
+ * POT is importable, against ot.emd2 itself in tests/test_oracle_vs_pot.py.
  *
  * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline /
  * --impl reference legs may load this library.

@@ -11,7 +11,8 @@
  * in the *reference form* (the Gibbs kernel is rebuilt from alpha/beta, the
  * error is taken from the log-form plan).  A NumPy twin lives in
  * oracle/pilot_oracle.py (sinkhorn_stabilized_np); the two are cross-checked
- * in tests/test_oracle_sinkhorn.py.  Parity against POT itself is UNPINNED.
+ * in tests/test_oracle_ot.py.  Parity against POT itself is UNPINNED here; wherever POT is
+ * importable tests/test_oracle_vs_pot.py checks both against ot.sinkhorn2.
  *
  * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline /
  * --impl reference legs may load this library.
