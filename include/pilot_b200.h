@@ -197,6 +197,23 @@ int pilot_knn_rows(const double *gram, int S, int k, int32_t *idx, double *dist,
                    void *workspace, size_t workspace_bytes, void *stream);
 
 /*
+ * (f-2) Silhouette coefficient of every sample on the dense S x S matrix: the arithmetic of
+ * Sil_computing(EMD, labels, metric) = sklearn.metrics.silhouette_score(EMD, labels, metric=metric)
+ * (Trajectory.py:593-612; called at :107-113 and per resolution in ploting.py:310-324, :420-439), the ROWS of the
+ * matrix as S-dimensional points.
+ * metric = PILOT_METRIC_COSINE or PILOT_METRIC_EUCLIDEAN: `matrix` is the Gram matrix X X^T of the points (a plain
+ * library GEMM on the caller's side); metric = PILOT_SIL_PRECOMPUTED: `matrix` is the distance matrix itself.
+ * The samples come grouped by cluster: perm[S] lists the sample indices sorted by label, seg[n_labels + 1] are the
+ * segment bounds inside perm, label[S] the compact label (0 .. n_labels - 1) of every sample.
+ * Output sil[S]: (b - a) / max(a, b), 0 for singleton clusters; the score is their mean.
+ * workspace: at least S doubles.  2 <= n_labels <= min(S - 1, 4096).
+ */
+#define PILOT_SIL_PRECOMPUTED 100
+int pilot_silhouette_rows(const double *matrix, int S, int metric, const int32_t *perm, const int32_t *seg,
+                          const int32_t *label, int n_labels, double *sil, void *workspace,
+                          size_t workspace_bytes, void *stream);
+
+/*
  * Pipe-peak microbenchmarks used as roofline denominators:
  * kind 0 = FP64 FMA, 1 = FP32 FMA, 2 = FP64 mma.sync (DMMA m8n8k4).
  * Runs on `stream`, returns achieved TFLOP/s in *h_tflops (host pointer).

@@ -13,7 +13,7 @@ from __future__ import annotations
 import sys
 
 from . import _lib, ops, pairs, pl, tl  # noqa: F401
-from .tl import (Cluster_Representations, Precomputed_distance, cost_matrix,  # noqa: F401
+from .tl import (Cluster_Representations, Precomputed_distance, Sil_computing, cost_matrix,  # noqa: F401
                  extract_data_anno_pathomics_from_h5ad, extract_data_anno_scRNA_from_h5ad, return_real_labels,
                  set_path_for_results, wasserstein_d, wasserstein_distance)
 
@@ -21,7 +21,8 @@ __version__ = "0.1.0"
 
 _PATCHED = ("wasserstein_distance", "Cluster_Representations", "cost_matrix", "wasserstein_d",
             "return_real_labels", "extract_data_anno_scRNA_from_h5ad",
-            "extract_data_anno_pathomics_from_h5ad", "set_path_for_results", "Precomputed_distance")
+            "extract_data_anno_pathomics_from_h5ad", "set_path_for_results", "Precomputed_distance",
+            "Sil_computing")
 
 
 def install() -> list:

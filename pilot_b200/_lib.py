@@ -35,11 +35,13 @@ def precision_code(precision) -> int:
         raise ValueError(f"precision must be 'f64' or 'f32', got {precision!r}") from None
 ST_CONVERGED, ST_MAXITER, ST_NUMERIC, ST_UNBOUNDED = 0, 1, 2, 3
 WS_MEDIAN, WS_SINKHORN, WS_EMD = 0, 1, 2
+SIL_PRECOMPUTED = 100
 
 EXPORTS = (
     "pilot_abi_version", "pilot_last_error", "pilot_range_count", "pilot_workspace_bytes", "pilot_launch_count",
     "pilot_hist", "pilot_props_finalize", "pilot_centroid_median", "pilot_cdist",
-    "pilot_sinkhorn_pairs", "pilot_emd_pairs", "pilot_unpack_pairs", "pilot_knn_rows", "pilot_pipe_peak",
+    "pilot_sinkhorn_pairs", "pilot_emd_pairs", "pilot_unpack_pairs", "pilot_knn_rows", "pilot_silhouette_rows",
+    "pilot_pipe_peak",
 )
 
 
@@ -96,6 +98,8 @@ def lib():
     L.pilot_unpack_pairs.argtypes = [vp, i64, i32, prp, dbl, vp, vp]
     L.pilot_knn_rows.restype = i32
     L.pilot_knn_rows.argtypes = [vp, i32, i32, vp, vp, vp, sz, vp]
+    L.pilot_silhouette_rows.restype = i32
+    L.pilot_silhouette_rows.argtypes = [vp, i32, i32, vp, vp, vp, i32, vp, vp, sz, vp]
     L.pilot_pipe_peak.restype = i32
     L.pilot_pipe_peak.argtypes = [i32, ctypes.POINTER(ctypes.c_double), vp]
     if L.pilot_abi_version() != ABI_VERSION:

@@ -192,12 +192,12 @@ extern "C" int pilot_hist(const int32_t *ct_code, const int32_t *smp_code, int64
     if (n_cells == 0) return 0;
     const size_t first_bytes = (size_t)(K + S) * sizeof(unsigned long long);
     const size_t smem_counts = first_bytes + (size_t)sk * sizeof(unsigned int);
-    const bool use_smem = smem_counts <= 96 * 1024;  // two CTAs per SM stay resident
+    const bool use_smem = smem_counts <= 200 * 1024;  // up to 110 KB two CTAs per SM stay resident, beyond that one
     const size_t smem = use_smem ? smem_counts : first_bytes;
     PILOT_CHECK_ARG(smem <= 200 * 1024, "pilot_hist: K+S=%d too large for shared first-index table", K + S);
     const long long warps_needed = ((n_cells >> 2) + 31) / 32;
     long long ctas = (warps_needed + (HIST_THREADS / 32) - 1) / (HIST_THREADS / 32);
-    const long long max_ctas = (long long)sm_count() * (use_smem && smem > 48 * 1024 ? 2 : 4);
+    const long long max_ctas = (long long)sm_count() * (use_smem && smem > 110 * 1024 ? 1 : (use_smem && smem > 48 * 1024 ? 2 : 4));
     if (ctas > max_ctas) ctas = max_ctas;
     if (ctas < 1) ctas = 1;
     if (use_smem) {

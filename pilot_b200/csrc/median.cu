@@ -4,11 +4,12 @@
 // NaNs ignored, even counts -> (lo + hi) / 2 rounded in the input dtype).
 //
 // Two exact paths:
-//  * sampled-pivot streaming path in natural row order (default for n >= 64K; second half of this file):
-//    a hashed sample of ~2048 rows per type gives, per (type, dim), two pivots lo <= hi that bracket the
-//    median with ~4e-8 failure odds; ONE coalesced pass over X in memory order then counts x < lo and
-//    x > hi in shared-memory counters and appends the ~12 % of elements inside the bracket to per-pair
-//    lists; a one-CTA-per-pair kernel finishes the selection inside the list.  If a pair's rank falls
+//  * sampled-pivot streaming path (default for n >= 64K; second half of this file):
+//    a hashed sample of ~2048-4096 rows per type gives, per (type, dim), two pivots lo <= hi that bracket the
+//    median with ~4e-8 failure odds; ONE pass over X then counts x < lo and collects the ~10 % of elements
+//    inside the bracket in per-pair lists (mn_stream_run_kernel: a CTA counting-sorts the row ids of a chunk
+//    of <= 4096 rows by type in shared memory, so that a lane walks rows of ONE type with its pivots in
+//    registers); a one-CTA-per-pair kernel finishes the selection inside the list.  If a pair's rank falls
 //    outside its bracket (or its list overflows) the same CTA falls back to an exact radix select over
 //    the type's rows -- no host round trip, results are always exact.
 //    HBM traffic: one read of X + ~6 % for the sample + the lists (written once, read once).
@@ -18,6 +19,7 @@
 // Two queries per (type, dim) (ranks (n-1)/2 and n/2) so even counts need no second selection.
 //
 // Algorithmic bytes: one read of X + codes.
+#include <type_traits>
 #include "common.cuh"
 
 namespace pilot {
@@ -227,30 +229,31 @@ static int median_run(const T *X, long long n, int D, long long ldx, const int *
 // =====================================================================================
 // sampled-pivot streaming path in NATURAL row order
 // =====================================================================================
-// Five small kernels around ONE coalesced pass over X:
+// Five small kernels around ONE pass over X:
 //   count   : cells per type (shared-memory histogram of the codes)
-//   plan    : per type the sampling stride, the candidate-list capacity and its offset in the pool
-//   sample  : ~2048 hashed rows per type copied into a type-major sample buffer (about 6 % of X)
+//   plan    : per type the sampling stride, the candidate-list capacity and its offset in the pool (one warp)
+//   sample  : ~2048-4096 hashed rows per type copied into a type-major sample buffer
 //   pivot   : per (type, dim) two pivots lo <= hi at the sample ranks n_s/2 -+ 2.75 sqrt(n_s): the true median
-//             lies outside with probability ~4e-8; the bracket holds ~12 % of the type's values
-//   stream  : X is read exactly once, in memory order (consecutive threads = consecutive elements, rows of any
-//             length or alignment coalesce); the pivots of every (type, dim) sit in shared memory; an element
-//             below lo / above hi bumps a shared-memory counter (lanes of a warp hit different dims: no
-//             conflicts), an element inside the closed bracket (or NaN) is appended to its (type, dim) list
-//             through one global atomic on the list cursor (~12 % of the elements; the cursors are L2 resident)
+//             lies outside with probability ~4e-8; the bracket holds ~9-12 % of the type's values
+//   stream  : X is read exactly once (mn_stream_run_kernel, below): x < lo bumps a per-lane counter, an element
+//             inside the closed bracket (or NaN) goes to a lane-private buffer and from there, once per item,
+//             to its (type, dim) list with one global atomic on the list cursor
 //   finish  : one CTA per (type, dim): rank bookkeeping (below / tie plateau / list / above), NaN count and radix
 //             select inside the list staged in shared memory; if the rank fell outside the bracket or the list
 //             overflowed, the same CTA runs an exact radix select over the type's rows -- no host round trip
-// Versus round 1 (rows gathered in type-sorted order): no counting sort of the row ids, no 200-byte row gathers
-// (which cost 1.35x the algorithmic bytes in partial sectors), three kernels fewer.
+// History of the stream pass (C3: 5 M x 50 f32, 40 types): round 1 gathered rows in GLOBAL type order (counting
+// sort of all row ids, 1.46x the algorithmic DRAM bytes); round 2a read X in memory order with 128-bit loads and
+// looked the pivots of every element up in shared memory (639 us, issue-bound at 78 instructions per element); a
+// column-thread variant fed by 1-D bulk copies (cp.async.bulk + mbarriers) cut that to 42 instructions and 500 us;
+// the chunk-sorted run form below needs ~15 and takes 376 us (2.7 TB/s), now bound by load latency.
 constexpr int MN_SAMPLE_MIN = 2048;     // target sample rows per type: n_k / 16 clamped to [MIN, MAX]
-constexpr int MN_SAMPLE_MAX = 8192;     //   (bracket width ~ 5.5 / sqrt(sample): 12 % ... 6 % of the type's values)
+constexpr int MN_SAMPLE_MAX = 4096;     //   (bracket width ~ 5.5 / sqrt(sample): 12 % ... 9 % of the type's values; measured best of 2048/4096/8192)
 constexpr int MN_MCAP = MN_SAMPLE_MAX + MN_SAMPLE_MAX / 4;  // most sample rows a type can hold (pivot kernel's buffer)
 constexpr double MED_SIGMAS = 5.5;      // half-width of the bracket in binomial sigmas
 constexpr int MN_THREADS = 512;         // stream kernel
 constexpr int MN_FIN_THREADS = 256;
 constexpr int MN_REP = 32;              // replicas of every (type, dim) list: same-address global atomics serialise at ~20 ns
-constexpr int MN_STAGE_BYTES = 65536;   // candidates staged in shared memory by the finish kernel
+constexpr int MN_STAGE_BYTES = 40960;   // candidates staged in shared memory by the finish kernel (5 CTAs per SM)
 constexpr size_t MN_SMEM_MAX = 160 * 1024;  // pivots + counters of every (type, dim) must fit
 
 // shared-memory reduction without the compiler's warp-aggregation collective
@@ -303,26 +306,39 @@ __global__ void msort_count_kernel(const int *__restrict__ code, long long n, in
 }
 
 
-template <typename T> __global__ void mn_plan_kernel(int K, int D, MnWs<T> ws)
+template <typename T> __global__ void mn_plan_kernel(int K, int D, int samp_max, MnWs<T> ws)
 {
-    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    // one warp: lane = type, 32 types per round, the two offsets by shuffle scans
+    if (blockIdx.x != 0 || threadIdx.x >= 32) return;
+    const int lane = threadIdx.x;
     unsigned long long off = 0, soff = 0;
-    for (int k = 0; k < K; ++k) {
-        const unsigned long long nk = ws.type_cnt[k];
+    for (int b0 = 0; b0 < K; b0 += 32) {
+        const int k = b0 + lane;
+        const unsigned long long nk = k < K ? ws.type_cnt[k] : 0ULL;
         const unsigned cap = (unsigned)(0.35 * (double)nk / MN_REP) + 64u;
         unsigned long long target = nk / 16;
-        target = target < MN_SAMPLE_MIN ? MN_SAMPLE_MIN : (target > MN_SAMPLE_MAX ? MN_SAMPLE_MAX : target);
+        target = target < MN_SAMPLE_MIN ? MN_SAMPLE_MIN : (target > (unsigned long long)samp_max ? (unsigned long long)samp_max : target);
         const unsigned long long sst = (nk + target - 1) / target;
-        ws.sstride[k] = (unsigned)(sst > 1 ? sst : 1);
         const unsigned long long expect = nk / (sst > 1 ? sst : 1);
         unsigned long long sc = expect + expect / 4 + 64;  // > 10 sigma of the binomial above the expectation
         if (sc > MN_MCAP) sc = MN_MCAP;
-        ws.scap[k] = (unsigned)sc;
-        ws.samp_off[k] = soff;
-        soff += sc;
-        ws.cap[k] = cap;
-        ws.cand_off[k] = off;
-        off += (unsigned long long)cap * (unsigned)D * MN_REP;
+        const unsigned long long mine_s = k < K ? sc : 0ULL;
+        const unsigned long long mine_c = k < K ? (unsigned long long)cap * (unsigned)D * MN_REP : 0ULL;
+        unsigned long long is = mine_s, ic = mine_c;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const unsigned long long vs = __shfl_up_sync(0xffffffffu, is, o), vc = __shfl_up_sync(0xffffffffu, ic, o);
+            if (lane >= o) { is += vs; ic += vc; }
+        }
+        if (k < K) {
+            ws.sstride[k] = (unsigned)(sst > 1 ? sst : 1);
+            ws.scap[k] = (unsigned)sc;
+            ws.samp_off[k] = soff + is - mine_s;
+            ws.cap[k] = cap;
+            ws.cand_off[k] = off + ic - mine_c;
+        }
+        soff += __shfl_sync(0xffffffffu, is, 31);
+        off += __shfl_sync(0xffffffffu, ic, 31);
     }
 }
 
@@ -347,8 +363,10 @@ __global__ void __launch_bounds__(256)
 mn_sample_kernel(const T *__restrict__ X, long long n, int D, long long ldx, const int *__restrict__ code, int K,
                  MnWs<T> ws)
 {
-    extern __shared__ unsigned int s_u[];  // cnt[K], base[K]
-    unsigned int *s_cnt = s_u, *s_base = s_u + K;
+    extern __shared__ __align__(16) unsigned int s_u[];  // cnt[K], base[K], sstride[K], scap[K], samp_off[K] (u64)
+    unsigned int *s_cnt = s_u, *s_base = s_u + K, *s_sst = s_u + 2 * K, *s_scap = s_u + 3 * K;
+    unsigned long long *s_soff = reinterpret_cast<unsigned long long *>(s_u + 4 * K);
+    for (int i = threadIdx.x; i < K; i += blockDim.x) { s_sst[i] = ws.sstride[i]; s_scap[i] = ws.scap[i]; s_soff[i] = ws.samp_off[i]; }
     __shared__ unsigned int s_row[MN_SAMP_STAGE];
     __shared__ unsigned int s_kp[MN_SAMP_STAGE];  // type << 16 | position inside the CTA's share
     __shared__ unsigned int s_n;
@@ -362,7 +380,7 @@ mn_sample_kernel(const T *__restrict__ X, long long n, int D, long long ldx, con
         for (long long i = t0 + threadIdx.x; i < t1; i += blockDim.x) {
             const int k = __ldg(code + i);
             if ((unsigned)k < (unsigned)K) {
-                const unsigned sst = ws.sstride[k];
+                const unsigned sst = s_sst[k];
                 if (sst <= 1u || (mn_hash((unsigned)i) % sst) == 0u) {
                     const unsigned lp = atomicAdd(&s_cnt[k], 1u);
                     const unsigned e = atomicAdd(&s_n, 1u);
@@ -379,19 +397,30 @@ mn_sample_kernel(const T *__restrict__ X, long long n, int D, long long ldx, con
         __syncthreads();
         const unsigned ne = s_n < (unsigned)MN_SAMP_STAGE ? s_n : (unsigned)MN_SAMP_STAGE;
         // copy: thread t moves the elements t, t + 256, ... of the staged rows (row-major): consecutive threads read
-        // consecutive elements of a row, and every load is independent of the others
+        // consecutive elements of a row; eight independent loads in flight per thread (the gather is latency-bound)
         {
             const unsigned total = ne * (unsigned)D;
-            unsigned e = threadIdx.x / (unsigned)D, d = threadIdx.x % (unsigned)D;
-            const unsigned se = blockDim.x / (unsigned)D, sd = blockDim.x % (unsigned)D;
-            for (unsigned idx = threadIdx.x; idx < total; idx += blockDim.x) {
-                const unsigned kp = s_kp[e];
-                const unsigned k = kp >> 16, pos = s_base[k] + (kp & 0xffffu);
-                const unsigned scp = ws.scap[k];
-                // dim-major inside the type's block: the pivot kernel reads its column contiguously
-                if (pos < scp) ws.samp[ws.samp_off[k] * D + (size_t)d * scp + pos] = X[(long long)s_row[e] * ldx + d];
-                d += sd; e += se;
-                if (d >= (unsigned)D) { d -= D; ++e; }
+            constexpr int CB = 8;
+            for (unsigned idx0 = threadIdx.x; idx0 < total; idx0 += CB * blockDim.x) {
+                T v[CB];
+                size_t dst[CB];
+                bool ok[CB];
+#pragma unroll
+                for (int c = 0; c < CB; ++c) {
+                    const unsigned idx = idx0 + c * blockDim.x;
+                    ok[c] = idx < total;
+                    const unsigned e = ok[c] ? idx / (unsigned)D : 0u, d = ok[c] ? idx - e * (unsigned)D : 0u;
+                    const unsigned kp = s_kp[e];
+                    const unsigned k = kp >> 16, pos = s_base[k] + (kp & 0xffffu);
+                    const unsigned scp = s_scap[k];
+                    ok[c] = ok[c] && pos < scp;
+                    // dim-major inside the type's block: the pivot kernel reads its column contiguously
+                    dst[c] = s_soff[k] * D + (size_t)d * scp + pos;
+                    v[c] = ok[c] ? X[(long long)s_row[e] * ldx + d] : (T)0;
+                }
+#pragma unroll
+                for (int c = 0; c < CB; ++c)
+                    if (ok[c]) ws.samp[dst[c]] = v[c];
             }
         }
         __syncthreads();
@@ -579,122 +608,199 @@ mn_stream_kernel(const T *__restrict__ X, long long n, int D, long long ldx, con
     }
 }
 
-// The streaming pass, fast path (rows contiguous, X 16-byte aligned): 128-bit loads, and the bracket candidates of a
-// warp are first compacted into a per-warp ring in shared memory and then appended 32 at a time with every lane
-// busy -- the divergent one-candidate-in-eight path of the scalar kernel cost more than the rest of the loop.
-constexpr int MN_RING = 256;  // entries per warp (an iteration adds at most 32 * 4)
+// The streaming pass, run form (any row stride or alignment): a CTA takes a chunk of <= 4096 consecutive rows,
+// counting-sorts the chunk's row ids by type in shared memory (codes only: 4 bytes per row), and its warps then
+// pull (type, 32-column group, 128-row segment) items: inside an item every row has the SAME type, so a lane keeps
+// the (lo, hi) pivots of its (type, dim) in registers and an element costs a shared-memory broadcast of the row id,
+// one address multiply-add, the load (a warp reads 32 consecutive elements of one row), two compares and a
+// predicated store -- about 10 instructions against 40-75 in the forms above, which look up the pivots per
+// element.  Bracket candidates collect in a lane-private shared-memory buffer and are appended to the (type, dim)
+// list once per item: ONE global atomic per lane and item instead of one per candidate.  The rows of a chunk are
+// read within microseconds of each other by one CTA, so the sectors two neighbouring rows share are fetched
+// from DRAM once (round 1 gathered rows in GLOBAL type order and paid 1.46x).
+constexpr int MN_RUN_THREADS = 512;
+constexpr int MN_RUN_CMAX = 4096;      // rows per chunk: ids fit u16, <= 8 rows per thread in the sort
+constexpr int MN_RUN_SEG = 128;        // rows per item
+template <typename T> struct MnRun {
+    static constexpr int B = 128 / (int)sizeof(T);  // lane-private candidate buffer entries (32 f32 / 16 f64)
+    static constexpr int U = 32 / (int)sizeof(T);   // loads in flight per lane (8 / 4)
+};
+
 template <typename T>
-__global__ void __launch_bounds__(MN_THREADS)
-mn_stream_vec_kernel(const T *__restrict__ X, long long n, int D, const int *__restrict__ code, int K, MnWs<T> ws)
+__global__ void __launch_bounds__(MN_RUN_THREADS, 2)
+mn_stream_run_kernel(const T *__restrict__ X, long long n, int D, long long ldx, const int *__restrict__ code, int K,
+                     int C, MnWs<T> ws)
 {
-    constexpr int V = 16 / (int)sizeof(T);  // elements per 128-bit load
+    constexpr int B = MnRun<T>::B, U = MnRun<T>::U, NT = MN_RUN_THREADS;
     extern __shared__ __align__(16) unsigned char smem_raw[];
+    T *buf = reinterpret_cast<T *>(smem_raw);                                   // [B][NT]
+    unsigned int *s_off = reinterpret_cast<unsigned int *>(buf + (size_t)B * NT);  // [K + 1] first sorted slot of a type
+    unsigned int *s_pos = s_off + K + 1;                                        // [K] counts, then scatter cursors
+    unsigned int *s_eoff = s_pos + K;                                           // [K + 1] first item-table entry of a type
+    unsigned int *s_tab = s_eoff + K + 1;                                       // [K + C / SEG + 1] type | segment << 16
+    unsigned short *s_rid = reinterpret_cast<unsigned short *>(s_tab + K + C / MN_RUN_SEG + 1);  // [C]
+    __shared__ unsigned int s_item, s_nitems;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int KD = K * D;
-    T *spiv = reinterpret_cast<T *>(smem_raw);                                  // [KD][2]
-    unsigned long long *scoff = reinterpret_cast<unsigned long long *>(spiv + 2 * (size_t)KD);  // [K]
-    unsigned int *sbelow = reinterpret_cast<unsigned int *>(scoff + K);         // [KD]
-    unsigned int *sties = sbelow + KD;                                          // [KD]
-    unsigned int *scap = sties + KD;                                            // [K]
-    T *rval = reinterpret_cast<T *>(scap + K + (K & 1));                        // [warps][MN_RING]
-    unsigned int *rkey = reinterpret_cast<unsigned int *>(rval + (MN_THREADS / 32) * MN_RING);
-    for (int i = threadIdx.x; i < 2 * KD; i += blockDim.x) spiv[i] = ws.piv[i];
-    for (int i = threadIdx.x; i < KD; i += blockDim.x) { sbelow[i] = 0u; sties[i] = 0u; }
-    for (int i = threadIdx.x; i < K; i += blockDim.x) { scoff[i] = ws.cand_off[i]; scap[i] = ws.cap[i]; }
-    __syncthreads();
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const unsigned lt_mask = (1u << lane) - 1u;
-    T *wval = rval + warp * MN_RING;
-    unsigned int *wkey = rkey + warp * MN_RING;
-    unsigned head = 0, count = 0;  // warp-uniform ring state
-
-    // append the first `m` (<= 32) ring entries: one lane per candidate
-    auto flush32 = [&](unsigned m) {
-        if ((unsigned)lane < m) {
-            const unsigned at = (head + lane) & (MN_RING - 1);
-            const unsigned key = wkey[at];
-            const T x = wval[at];
-            const unsigned k = key & 0xfffu, dd = (key >> 12) & 0xfffu, rep = key >> 24;
-            const unsigned kd = k * (unsigned)D + dd;
-            const unsigned pos = atomicAdd(&ws.ncand[(size_t)rep * KD + kd], 1u);
-            const unsigned cap = scap[k];
-            if (pos < cap) ws.cand[scoff[k] + (size_t)(rep * (unsigned)D + dd) * cap + pos] = x;
-        }
-        head += m;
-        count -= m;
-    };
-
-    const long long E = n * (long long)D;
-    const long long Q = (E + V - 1) / V;
-    const long long per = (Q + gridDim.x - 1) / gridDim.x;
-    const long long q0 = (long long)blockIdx.x * per;
-    const long long q1 = q0 + per < Q ? q0 + per : Q;
-    const int NT = blockDim.x;
-    long long e = (q0 + threadIdx.x) * V;
-    long long row = e / D;
-    int d = (int)(e - row * D);
-    const int step_r = (NT * V) / D, step_d = (NT * V) % D;
-    const long long e_end = q1 * V < E ? q1 * V : E;
-    // every warp runs the same number of iterations (the ballots need all lanes)
-    const long long iters = (q1 - q0 + NT - 1) / NT;
-    for (long long it = 0; it < iters; ++it) {
-        T x[V];
-        const bool in = e + V <= e_end;
-        if (in) {
-            const int4 raw = *reinterpret_cast<const int4 *>(X + e);
-            if (V == 4) {
-                x[0] = (T)__int_as_float(raw.x); x[1] = (T)__int_as_float(raw.y);
-                x[V - 2] = (T)__int_as_float(raw.z); x[V - 1] = (T)__int_as_float(raw.w);
-            } else {
-                x[0] = (T)__hiloint2double(raw.y, raw.x);
-                x[V - 1] = (T)__hiloint2double(raw.w, raw.z);
-            }
-        } else {
+    const int CG = (D + 31) >> 5;
+    const long long chunks = (n + C - 1) / C;
+    for (long long chunk = blockIdx.x; chunk < chunks; chunk += gridDim.x) {
+        const long long row0 = chunk * C;
+        const int rows = (int)(n - row0 < C ? n - row0 : C);
+        // ---- counting sort of the chunk's row ids by type ----
+        for (int i = tid; i < K; i += NT) s_pos[i] = 0u;
+        if (tid == 0) s_item = 0u;
+        __syncthreads();
+        int kreg[MN_RUN_CMAX / NT];
 #pragma unroll
-            for (int j = 0; j < V; ++j) x[j] = e + j < e_end ? X[e + j] : (T)0;
+        for (int j = 0; j < MN_RUN_CMAX / NT; ++j) {
+            const int i = tid + j * NT;
+            int k = i < rows ? __ldg(code + row0 + i) : -1;
+            if ((unsigned)k >= (unsigned)K) k = -1;
+            kreg[j] = k;
+            if (k >= 0) atomicAdd(&s_pos[k], 1u);
         }
-        const bool any = e < e_end;
-        const int k0 = any ? __ldg(code + row) : -1;
-        const int wrap_at = D - d;  // elements j >= wrap_at belong to the next row
-        const int k1 = (any && wrap_at < V && row + 1 < n) ? __ldg(code + row + 1) : -1;
-        const unsigned rep0 = mn_rep((unsigned)row) << 24, rep1 = mn_rep((unsigned)row + 1u) << 24;
-        const int nvalid = in ? V : (any ? (int)(e_end - e) : 0);
+        __syncthreads();
+        if (warp == 0) {  // exclusive scans of the counts and of the segment counts
+            unsigned run = 0, erun = 0;
+            for (int b0 = 0; b0 < K; b0 += 32) {
+                const int k = b0 + lane;
+                const unsigned c = k < K ? s_pos[k] : 0u;
+                const unsigned e = (c + MN_RUN_SEG - 1) / MN_RUN_SEG;
+                unsigned ic = c, ie = e;
 #pragma unroll
-        for (int j = 0; j < V; ++j) {
-            const bool w = j >= wrap_at;
-            const int dj = w ? d + j - D : d + j;
-            const int kj = w ? k1 : k0;
-            const bool valid = j < nvalid && (unsigned)kj < (unsigned)K;
-            const int kd = valid ? kj * D + dj : 0;
-            const T lo = spiv[2 * kd], hi = spiv[2 * kd + 1];
-            const bool lt = x[j] < lo, ge = !(x[j] > hi);
-            if (valid && lt) red_shared_inc(&sbelow[kd]);
-            bool cand = valid && !lt && ge;              // the closed bracket [lo, hi] and every NaN ...
-            if (cand && lo == hi && x[j] == lo) {        // ... except the ties of a plateau lo == hi: counted
-                red_shared_inc(&sties[kd]);
-                cand = false;
+                for (int o = 1; o < 32; o <<= 1) {
+                    const unsigned vc = __shfl_up_sync(0xffffffffu, ic, o), ve = __shfl_up_sync(0xffffffffu, ie, o);
+                    if (lane >= o) { ic += vc; ie += ve; }
+                }
+                if (k < K) {
+                    s_off[k] = run + ic - c;
+                    s_pos[k] = run + ic - c;
+                    s_eoff[k] = erun + ie - e;
+                    for (unsigned sgm = 0; sgm < e; ++sgm) s_tab[erun + ie - e + sgm] = (unsigned)k | (sgm << 16);
+                }
+                run += __shfl_sync(0xffffffffu, ic, 31);
+                erun += __shfl_sync(0xffffffffu, ie, 31);
             }
-            const unsigned bal = __ballot_sync(0xffffffffu, cand);
-            if (cand) {
-                const unsigned at = (head + count + __popc(bal & lt_mask)) & (MN_RING - 1);
-                wval[at] = x[j];
-                wkey[at] = (unsigned)kj | ((unsigned)dj << 12) | (w ? rep1 : rep0);
-            }
-            count += __popc(bal);
+            if (lane == 0) { s_off[K] = run; s_eoff[K] = erun; s_nitems = erun * (unsigned)CG; }
         }
-        __syncwarp();
-        while (count >= 32u) flush32(32u);
-        __syncwarp();
-        e += (long long)NT * V;
-        d += step_d;
-        row += step_r;
-        if (d >= D) { d -= D; ++row; }
-    }
-    if (count) flush32(count);
-    __syncthreads();
-    for (int i = threadIdx.x; i < KD; i += blockDim.x) {
-        const unsigned b = sbelow[i], t = sties[i];
-        if (b) atomicAdd(&ws.below[i], b);
-        if (t) atomicAdd(&ws.above[i], t);
+        __syncthreads();
+#pragma unroll
+        for (int j = 0; j < MN_RUN_CMAX / NT; ++j) {
+            const int k = kreg[j];
+            if (k >= 0) s_rid[atomicAdd(&s_pos[k], 1u)] = (unsigned short)(tid + j * NT);
+        }
+        __syncthreads();
+        // ---- items ----
+        const unsigned nitems = s_nitems;
+        const T *xrow0 = X + row0 * ldx;
+        const unsigned ldxb = (unsigned)ldx * (unsigned)sizeof(T);  // chunk-relative byte offsets stay below 2^32
+        for (;;) {
+            unsigned item = 0;
+            if (lane == 0) item = atomicAdd(&s_item, 1u);
+            item = __shfl_sync(0xffffffffu, item, 0);
+            if (item >= nitems) break;
+            const unsigned ent = s_tab[item / (unsigned)CG], cg = item % (unsigned)CG;
+            const int k = (int)(ent & 0xffffu), sgm = (int)(ent >> 16);
+            // list replica: by chunk and segment, so that a type whose rows sit in a few chunks (type-sorted input)
+            // still spreads over all replicas
+            const unsigned rep = (unsigned)(chunk + (chunk >> 5) + sgm) & (MN_REP - 1);
+            const unsigned first = s_off[k] + (unsigned)sgm * MN_RUN_SEG;
+            const unsigned tcnt = s_off[k + 1] - first;
+            const int cnt = (int)(tcnt < (unsigned)MN_RUN_SEG ? tcnt : (unsigned)MN_RUN_SEG);
+            const unsigned short *rid = s_rid + first;
+            // lane -> (row slot, column): a column group narrower than 17 takes several rows per step
+            const int Wc = D - (int)cg * 32 < 32 ? D - (int)cg * 32 : 32;
+            const int RPS = 32 / Wc;
+            const int sub = lane / Wc, d = (int)cg * 32 + (lane - sub * Wc);
+            const bool active = sub < RPS;
+            const int kd = k * D + (active ? d : 0);
+            // a lane without a column compares against an empty bracket: it never lists anything that matters
+            const T lo = active ? ws.piv[2 * kd] : Inf<T>::pos(), hi = active ? ws.piv[2 * kd + 1] : -Inf<T>::pos();
+            const bool tie = active && lo == hi;
+            const unsigned char *xpb = reinterpret_cast<const unsigned char *>(xrow0 + (active ? d : 0));
+            const int subz = active ? sub : 0;
+            const bool any_tie = __any_sync(0xffffffffu, tie);
+            unsigned below = 0, ties = 0, nb = 0;
+            T *mybuf = buf + tid;
+
+            auto flush_all = [&]() {
+                if (active && nb) {
+                    const unsigned pos = atomicAdd(&ws.ncand[(size_t)rep * KD + kd], nb);
+                    const unsigned cap = ws.cap[k];
+                    T *dst = ws.cand + ws.cand_off[k] + (size_t)(rep * (unsigned)D + (unsigned)d) * cap;
+                    for (unsigned j = 0; j < nb; ++j)
+                        if (pos + j < cap) dst[pos + j] = mybuf[(size_t)j * NT];
+                }
+                nb = 0;
+            };
+            // the closed bracket [lo, hi] and every NaN are listed; TIES: the ties of a plateau lo == hi are counted
+            auto element = [&](T x, auto ties_tag) {
+                const bool lt = x < lo;
+                below += lt ? 1u : 0u;
+                bool cand = !lt && !(x > hi);
+                if (decltype(ties_tag)::value) {
+                    if (tie && cand && x == lo) {
+                        ++ties;
+                        cand = false;
+                    }
+                }
+                if (cand) {
+                    mybuf[(size_t)nb * NT] = x;
+                    ++nb;
+                }
+            };
+            auto load_batch = [&](int j0, T (&x)[U]) {
+#pragma unroll
+                for (int u = 0; u < U; ++u)
+                    x[u] = *reinterpret_cast<const T *>(xpb + (unsigned)rid[j0 + u * RPS + subz] * ldxb);
+            };
+            auto run_batch = [&](T (&x)[U]) {
+                if (any_tie) {
+#pragma unroll
+                    for (int u = 0; u < U; ++u) element(x[u], std::true_type());
+                } else {
+#pragma unroll
+                    for (int u = 0; u < U; ++u) element(x[u], std::false_type());
+                }
+                if (__any_sync(0xffffffffu, nb > (unsigned)(B - U))) flush_all();
+            };
+            const int stepr = RPS * U;
+            const int nfull = cnt / stepr;
+            // whole batches, software-pipelined: the loads of the next batch are in flight while this one is compared
+            if (nfull > 0) {
+                T xa[U], xb[U];
+                load_batch(0, xa);
+                int bi = 0;
+                for (; bi + 2 <= nfull; bi += 2) {
+                    load_batch((bi + 1) * stepr, xb);
+                    run_batch(xa);
+                    if (bi + 2 < nfull) load_batch((bi + 2) * stepr, xa);
+                    run_batch(xb);
+                }
+                if (bi < nfull) run_batch(xa);
+            }
+            const int j0 = nfull * stepr;
+            if (j0 < cnt) {  // the short last batch
+                T x[U];
+                bool ok[U];
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    const int j = j0 + u * RPS + sub;
+                    ok[u] = active && j < cnt;
+                    x[u] = ok[u] ? *reinterpret_cast<const T *>(xpb + (unsigned)rid[j] * ldxb) : (T)0;
+                }
+#pragma unroll
+                for (int u = 0; u < U; ++u)
+                    if (ok[u]) element(x[u], std::true_type());
+            }
+            flush_all();
+            if (active) {
+                if (below) atomicAdd(&ws.below[kd], below);
+                if (ties) atomicAdd(&ws.above[kd], ties);
+            }
+        }
+        __syncthreads();
     }
 }
 
@@ -751,10 +857,18 @@ mn_finish_kernel(const T *__restrict__ X, long long n, int D, long long ldx, con
         for (int r = warp; r < MN_REP; r += MN_FIN_THREADS / 32) {
             const unsigned o = s_roff[r], c = s_roff[r + 1] - o;
             const T *src = cl + (size_t)r * rstride;
-            for (unsigned i = lane; i < c; i += 32) f(o + i, src[i]);
+            for (unsigned i0 = lane; i0 < c; i0 += 128) {  // four independent loads in flight per lane
+                T v[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) v[u] = i0 + 32 * u < c ? src[i0 + 32 * u] : (T)0;
+#pragma unroll
+                for (int u = 0; u < 4; ++u)
+                    if (i0 + 32 * u < c) f(o + i0 + 32 * u, v[u]);
+            }
         }
     };
-    if (staged) lst_raw([&](unsigned at, T x) { s_stage[at] = x; });
+    unsigned my_nan = 0;
+    if (staged) lst_raw([&](unsigned at, T x) { s_stage[at] = x; my_nan += x != x ? 1u : 0u; });  // NaNs counted on the way
     __syncthreads();
     auto lst_all = [&](auto f) {
         if (staged) {
@@ -765,8 +879,8 @@ mn_finish_kernel(const T *__restrict__ X, long long n, int D, long long ldx, con
     };
     long long n_nan = 0;
     if (!overflow) {
-        unsigned my = 0;
-        lst_all([&](T x) { my += x != x ? 1u : 0u; });
+        unsigned my = my_nan;
+        if (!staged) lst_all([&](T x) { my += x != x ? 1u : 0u; });
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) my += __shfl_xor_sync(0xffffffffu, my, o);
         if ((threadIdx.x & 31) == 0 && my) atomicAdd(&s_nan, (unsigned long long)my);
@@ -850,6 +964,12 @@ mn_finish_kernel(const T *__restrict__ X, long long n, int D, long long ldx, con
 
 static size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
 
+constexpr size_t MN_RUN_SMEM_MAX = 100 * 1024;  // two CTAs per SM
+template <typename T> static size_t mn_run_smem(int K, long long C)
+{
+    return (size_t)MnRun<T>::B * MN_RUN_THREADS * sizeof(T) + ((size_t)4 * K + 3 + C / MN_RUN_SEG + 1) * 4 + (size_t)C * 2 + 16;
+}
+
 static size_t mn_stream_smem(int K, int D, size_t elt)
 {
     const size_t kd = (size_t)K * D;
@@ -903,39 +1023,51 @@ static int median_run_stream(const T *X, long long n, int D, long long ldx, cons
     if (blocks < 1) blocks = 1;
     msort_count_kernel<<<(unsigned)blocks, 256, K * sizeof(unsigned int), st>>>(code, n, K, ws.type_cnt);
     PILOT_LAUNCH_CHECK();
-    mn_plan_kernel<T><<<1, 32, 0, st>>>(K, D, ws);
+    mn_plan_kernel<T><<<1, 32, 0, st>>>(K, D, MN_SAMPLE_MAX, ws);
     PILOT_LAUNCH_CHECK();
     {
         long long sblocks = (n + 1023) / 1024;  // one global atomic per (CTA, type): ~20 ns each, serialised per type
         if (sblocks > 4LL * sm_count()) sblocks = 4LL * sm_count();
-        mn_sample_kernel<T><<<(unsigned)sblocks, 256, 2 * K * sizeof(unsigned int), st>>>(X, n, D, ldx, code, K, ws);
+        mn_sample_kernel<T><<<(unsigned)sblocks, 256, (6 * (size_t)K + 2) * sizeof(unsigned int), st>>>(X, n, D, ldx, code, K, ws);
     }
     PILOT_LAUNCH_CHECK();
     PILOT_CUDA(cudaFuncSetAttribute(mn_pivot_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                     (int)(MN_MCAP * sizeof(T))));
     mn_pivot_kernel<T><<<(unsigned)kd, 256, MN_MCAP * sizeof(T), st>>>(D, ws);
     PILOT_LAUNCH_CHECK();
-    {
-        // fast path: contiguous rows, 16-byte aligned, a 128-bit vector spans at most two rows
-        const bool vec = ldx == D && ((uintptr_t)X % 16) == 0 && D >= 16 / (int)sizeof(T) && K <= 4096 && D <= 4096;
-        const size_t ring = vec ? (size_t)(MN_THREADS / 32) * MN_RING * (sizeof(T) + 4) + 8 : 0;
-        const size_t smem = mn_stream_smem(K, D, sizeof(T)) + ring;
-        int per_sm = 1;
-        if (vec) {
-            PILOT_CUDA(cudaFuncSetAttribute(mn_stream_vec_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            PILOT_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, mn_stream_vec_kernel<T>, MN_THREADS, smem));
-        } else {
-            PILOT_CUDA(cudaFuncSetAttribute(mn_stream_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            PILOT_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, mn_stream_kernel<T>, MN_THREADS, smem));
+    bool streamed = false;
+    if (K <= 32768 && ldx * (long long)sizeof(T) < (1LL << 20)) {  // chunk-relative byte offsets stay below 2^32
+        // run form: chunk-sorted row ids, pivots in registers
+        const long long cta_cap = (long long)sm_count() * 2;
+        long long ctas = (n + 1023) / 1024;           // chunks of at least ~1024 rows
+        if (ctas > cta_cap) ctas = cta_cap;
+        const long long m = (n + ctas * MN_RUN_CMAX - 1) / (ctas * MN_RUN_CMAX);   // chunks per CTA
+        long long C = (n + ctas * m - 1) / (ctas * m);
+        C = (C + 7) & ~7LL;
+        if (C > MN_RUN_CMAX) C = MN_RUN_CMAX;
+        const size_t smem = mn_run_smem<T>(K, C);
+        if (smem <= MN_RUN_SMEM_MAX) {
+            PILOT_CUDA(cudaFuncSetAttribute(mn_stream_run_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            const long long chunks = (n + C - 1) / C;
+            if (ctas > chunks) ctas = chunks;
+            mn_stream_run_kernel<T><<<(unsigned)ctas, MN_RUN_THREADS, smem, st>>>(X, n, D, ldx, code, K, (int)C, ws);
+            PILOT_LAUNCH_CHECK();
+            streamed = true;
         }
+    }
+    if (!streamed) {
+        // element-thread form (huge row strides or type counts): pivots and counters of every (type, dim) in shared memory
+        const size_t smem = mn_stream_smem(K, D, sizeof(T));
+        int per_sm = 1;
+        PILOT_CUDA(cudaFuncSetAttribute(mn_stream_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        PILOT_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, mn_stream_kernel<T>, MN_THREADS, smem));
         if (per_sm < 1) per_sm = 1;
         if (per_sm > 4) per_sm = 4;
         long long ctas = (long long)sm_count() * per_sm;
         const long long need = (n * D + (long long)MN_THREADS * 16 - 1) / ((long long)MN_THREADS * 16);
         if (ctas > need) ctas = need;
         if (ctas < 1) ctas = 1;
-        if (vec) mn_stream_vec_kernel<T><<<(unsigned)ctas, MN_THREADS, smem, st>>>(X, n, D, code, K, ws);
-        else     mn_stream_kernel<T><<<(unsigned)ctas, MN_THREADS, smem, st>>>(X, n, D, ldx, code, K, ws);
+        mn_stream_kernel<T><<<(unsigned)ctas, MN_THREADS, smem, st>>>(X, n, D, ldx, code, K, ws);
         PILOT_LAUNCH_CHECK();
     }
     PILOT_CUDA(cudaFuncSetAttribute(mn_finish_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, MN_STAGE_BYTES));
@@ -946,8 +1078,7 @@ static int median_run_stream(const T *X, long long n, int D, long long ldx, cons
 
 static bool median_use_sorted(long long n, int K, int D)
 {
-    return n >= 65536 && n < (1LL << 32) && K <= 4096 &&
-           mn_stream_smem(K, D, 8) + (size_t)(MN_THREADS / 32) * MN_RING * 12 + 8 <= MN_SMEM_MAX;
+    return n >= 65536 && n < (1LL << 32) && K <= 4096 && mn_stream_smem(K, D, 8) <= MN_SMEM_MAX;
 }
 
 size_t median_ws_bytes(long long n, int K, int D)

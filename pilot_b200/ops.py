@@ -11,6 +11,7 @@ from __future__ import annotations
 import ctypes
 from typing import Optional, Tuple
 
+import numpy as np
 import torch
 
 from . import _lib
@@ -219,6 +220,37 @@ def knn_rows(X: torch.Tensor, k: int) -> Tuple[torch.Tensor, torch.Tensor]:
     check(lib().pilot_knn_rows(_ptr(gram), S, int(k), _ptr(idx), _ptr(dist), _ptr(ws), ws.numel(), _stream()),
           "pilot_knn_rows")
     return idx, dist
+
+
+def silhouette_rows(X: torch.Tensor, labels, metric: str = "cosine") -> torch.Tensor:
+    """Silhouette coefficient of every row of X (S x S float64, rows = points; metric 'cosine' or 'euclidean') or
+    of every sample of the distance matrix X (metric 'precomputed') under the clustering ``labels``: float64 [S].
+    The Gram matrix is a library GEMM (torch.mm); distances and the per-cluster reductions run in
+    pilot_silhouette_rows.  Label bookkeeping (sklearn's LabelEncoder + a stable sort by label) is host NumPy."""
+    _require_cuda(X)
+    assert X.dim() == 2 and X.shape[0] == X.shape[1] and X.dtype == torch.float64
+    S = X.shape[0]
+    codes = np.unique(np.asarray(labels), return_inverse=True)[1].astype(np.int32).ravel()
+    if codes.shape[0] != S:
+        raise ValueError(f"Found input variables with inconsistent numbers of samples: [{S}, {codes.shape[0]}]")
+    L = int(codes.max()) + 1
+    if not 1 < L < S:
+        raise ValueError("Number of labels is %d. Valid values are 2 to n_samples - 1 (inclusive)" % L)
+    perm = np.argsort(codes, kind="stable").astype(np.int32)
+    seg = np.concatenate([[0], np.cumsum(np.bincount(codes, minlength=L))]).astype(np.int32)
+    if metric == "precomputed":
+        mid, mat = _lib.SIL_PRECOMPUTED, X.contiguous()
+    elif metric in ("cosine", "euclidean"):
+        mid, mat = _lib.METRICS[metric], torch.mm(X, X.t())
+    else:
+        raise ValueError(f"silhouette metric {metric!r}: 'cosine', 'euclidean' or 'precomputed' (no CPU fallback)")
+    dev = X.device
+    perm_d, seg_d, lab_d = (torch.from_numpy(a).to(dev) for a in (perm, seg, codes))
+    out = torch.empty(S, dtype=torch.float64, device=dev)
+    ws = _workspace(max(S * 8, 256), dev)
+    check(lib().pilot_silhouette_rows(_ptr(mat), S, int(mid), _ptr(perm_d), _ptr(seg_d), _ptr(lab_d), L, _ptr(out),
+                                      _ptr(ws), ws.numel(), _stream()), "pilot_silhouette_rows")
+    return out
 
 
 def pipe_peak(kind: int) -> float:

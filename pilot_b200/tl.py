@@ -484,16 +484,32 @@ def wasserstein_distance(adata, emb_matrix="X_PCA", clusters_col="cell_types", s
         adata.uns["real_labels"] = list(annot["status"].iloc[lab.first_smp])
 
 
+def Sil_computing(EMD, real_labels, metric="cosine"):
+    """Silhouette score of the samples (``Trajectory.py:593-612``: ``sklearn.metrics.silhouette_score(EMD,
+    real_labels, metric=metric)``, the ROWS of the matrix as points).  GPU: one library DGEMM for the Gram matrix,
+    distances and per-cluster reductions in ``pilot_silhouette_rows``.  ``EMD``: ndarray or CUDA
+    tensor; metrics 'cosine' (the reference's default), 'euclidean' and 'precomputed'."""
+    if not torch.cuda.is_available():
+        raise ops._lib.PilotLibraryError("pilot_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
+    E = EMD if isinstance(EMD, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(EMD, dtype=np.float64)).cuda()
+    if metric == "precomputed" and bool((torch.diagonal(E).abs() > 1e-10).any()):
+        raise ValueError("The precomputed distance matrix contains non-zero elements on the diagonal. "
+                         "Use np.fill_diagonal(X, 0).")           # scikit-learn's own check and message
+    sil = ops.silhouette_rows(E.contiguous(), real_labels, metric)
+    return float(sil.cpu().numpy().mean())
+
+
 def _require_clustering_tail():
-    """(Clustering, Sil_computing) of the reference (Trajectory.py:527-612).  They need scanpy, leidenalg and
-    scikit-learn and consume the finished matrix; this package does not re-implement graph clustering."""
+    """``Clustering`` of the reference (Trajectory.py:527-588): scanpy neighbours + Leiden + Rand index.  Graph
+    clustering is not re-implemented here (it needs scanpy and leidenalg and cannot be pinned without them); the
+    silhouette half of the tail is ``Sil_computing`` above."""
     try:
-        from pilotpy.tools.Trajectory import Clustering, Sil_computing  # type: ignore
+        from pilotpy.tools.Trajectory import Clustering  # type: ignore
     except Exception as exc:
         raise NotImplementedError(
-            "return_sil_ari=True runs the reference's Leiden/ARI/silhouette tail (Trajectory.py:107-113), which "
-            "needs pilotpy with scanpy + leidenalg importable; it is a consumer of the distance matrix, outside "
-            f"the patient-distance hot path (SURVEY.md 8f #2, #4).  Import failed with: {exc!r}") from exc
+            "return_sil_ari=True runs the reference's Leiden/ARI tail (Trajectory.py:107-113), which needs pilotpy "
+            "with scanpy + leidenalg importable; it is a consumer of the distance matrix, outside the "
+            f"patient-distance hot path (SURVEY.md 8f #2, #4).  Import failed with: {exc!r}") from exc
     return Clustering, Sil_computing
 
 
