@@ -24,6 +24,7 @@ import pandas as pd
 import torch
 
 from . import ops, pairs
+from .h5ad import load_h5ad  # noqa: F401  (pilotpy.tl.load_h5ad, Trajectory.py:121-137)
 
 warnings.filterwarnings("ignore")  # the reference silences everything at import (Trajectory.py:32)
 

@@ -1,5 +1,7 @@
 """End-to-end drop-in parity of pilot_b200.tl.wasserstein_distance on a duck-typed AnnData:
 the committed golden fixtures (reference outputs) and the oracle on BASELINE config C1."""
+import os
+
 import numpy as np
 import pandas as pd
 import pytest
@@ -33,6 +35,35 @@ def test_golden_fixture(name):
     assert [str(x) for x in u["real_labels"]] == list(g["real_labels"])
     assert list(u["annot"].columns) == ["cell_type", "sampleID", "status"]
     assert len(u["data"]) == len(u["annot"])
+
+
+def test_kidney_igan_real_data_golden():
+    """The reference's own test case (test/test_pilot.py:7-15) on REAL data: Kidney_IgAN_G.h5ad, 24 227 glomeruli x
+    14 features, 634 biopsies, data_type='Pathomics'.  Inputs and the reference's outputs were stored by
+    tests/golden/make_kidney_golden.py (reference functions exec'd verbatim on the file read by pilot_b200.h5ad)."""
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "g6_kidney_igan_G.npz"),
+                allow_pickle=True)
+    obs = pd.DataFrame({
+        "Cell_type": g["cell_type"],
+        "sampleID": pd.Categorical.from_codes(g["sample_codes"], categories=list(g["sample_categories"])),
+        "status": pd.Categorical.from_codes(g["status_codes"], categories=list(g["status_categories"])),
+    })
+    adata = synth.FakeAnnData(obs, X=g["X"], var_names=list(g["var_names"]))
+    tl.wasserstein_distance(adata, clusters_col="Cell_type", sample_col="sampleID", status="status",
+                            data_type="Pathomics")
+    u = adata.uns
+    assert [str(k) for k in u["proportions"].keys()] == list(g["samples"])
+    P = np.stack(list(u["proportions"].values()))
+    assert np.array_equal(P, g["props"]), "proportions must be bit-exact"
+    assert list(u["cost"].columns) == list(g["cells"])
+    np.testing.assert_allclose(u["cost"].to_numpy(), g["cost"], rtol=1e-12, atol=1e-15)
+    E = u["EMD"]
+    assert E.shape == (634, 634)
+    np.testing.assert_allclose(E[g["EMD_rows"]], g["EMD_sub"], rtol=1e-9, atol=1e-14)
+    np.testing.assert_allclose(E.sum(axis=0), g["EMD_colsum"], rtol=1e-10)
+    np.testing.assert_allclose(np.diag(E), g["EMD_diag"], atol=1e-14)
+    np.testing.assert_allclose(u["EMD_df"].to_numpy(), E.T, rtol=0, atol=0)
+    assert [str(x) for x in u["real_labels"]] == list(g["real_labels"])
 
 
 @pytest.mark.parametrize("labels", ["str", "categorical"])
