@@ -681,7 +681,14 @@ def run_cells(args):
     obs_str = obs.copy()
     for c in obs_str.columns:
         obs_str[c] = obs_str[c].astype(str).astype(object)
-    t_e2e_default = time_api(np.array(X, copy=True), obs_str, max(1, min(args.steps, 3)))
+    X_pageable = np.array(X, copy=True)
+    tl._factor_cache.clear()
+    torch.cuda.synchronize()
+    t0c = time.perf_counter()
+    api_step(X_pageable, obs_str)            # first call on these label objects: pays the string factorisation
+    torch.cuda.synchronize()
+    t_e2e_default_first = time.perf_counter() - t0c
+    t_e2e_default = time_api(X_pageable, obs_str, max(1, min(args.steps, 3)))
     code_bytes = sum(1 if c < 128 else (2 if c < 32768 else 4) for c in (k, s))
     h2d = n * code_bytes + X.nbytes + (k + s) * 4
     d2h = s * s * 8 + s * k * 8 + k * k * 8 + (k + s) * 8
@@ -702,8 +709,11 @@ def run_cells(args):
                     "d2h_bytes_per_step": int(d2h), "ms_per_step": t_e2e * 1e3,
                     "api": "pilot_b200.tl.wasserstein_distance(adata) with categorical obs and a pinned host embedding",
                     "default_inputs": {"value": units / t_e2e_default, "ms_per_step": t_e2e_default * 1e3,
-                                       "what": "pageable ndarray embedding and str label columns (the reference's "
-                                               "default user input, Trajectory.py:255-263)"}},
+                                       "first_call_ms": t_e2e_default_first * 1e3,
+                                       "what": "pageable ndarray embedding and str label columns, every cell its own "
+                                               "str object (the reference's default user input, Trajectory.py:255-263); "
+                                               "ms_per_step: repeated calls on the same label objects (validated "
+                                               "factorisation cache), first_call_ms: the call that factorises them"}},
             "gpu_launches": int(launches), "stage_ms": stage_ms, "roofline": roofline, "pipe_peaks": peaks}
     if world == 1:
         rows = max(1, min(s, 2000 // s + 1))

@@ -253,7 +253,7 @@ constexpr double MED_SIGMAS = 5.5;      // half-width of the bracket in binomial
 constexpr int MN_THREADS = 512;         // stream kernel
 constexpr int MN_FIN_THREADS = 256;
 constexpr int MN_REP = 32;              // replicas of every (type, dim) list: same-address global atomics serialise at ~20 ns
-constexpr int MN_STAGE_BYTES = 40960;   // candidates staged in shared memory by the finish kernel (5 CTAs per SM)
+constexpr int MN_STAGE_MIN = 16384, MN_STAGE_MAX = 98304;  // bytes of candidates the finish kernel stages in shared memory
 constexpr size_t MN_SMEM_MAX = 160 * 1024;  // pivots + counters of every (type, dim) must fit
 
 // shared-memory reduction without the compiler's warp-aggregation collective
@@ -285,7 +285,7 @@ template <typename T> struct MnWs {
     unsigned int *scap;                    // K: rows of the type's sample buffer
     unsigned long long *samp_off;          // K: first row of the type's sample buffer
     T *piv;                                // KD x 2
-    T *samp;                               // per type a block of D x scap[k] values, dim-major
+    T *samp;                               // per type a block of scap[k] sample rows of D values, row-major
     T *cand;                               // pool
 };
 
@@ -414,8 +414,10 @@ mn_sample_kernel(const T *__restrict__ X, long long n, int D, long long ldx, con
                     const unsigned k = kp >> 16, pos = s_base[k] + (kp & 0xffffu);
                     const unsigned scp = s_scap[k];
                     ok[c] = ok[c] && pos < scp;
-                    // dim-major inside the type's block: the pivot kernel reads its column contiguously
-                    dst[c] = s_soff[k] * D + (size_t)d * scp + pos;
+                    // row-major inside the type's block: whole-row (coalesced) writes.  A dim-major block cost a 32-byte
+                    // L2 sector per 4-byte element (15.6 M sector writes at C3, 165 us); the pivot kernel's strided column
+                    // reads hit L2
+                    dst[c] = (s_soff[k] + pos) * D + d;
                     v[c] = ok[c] ? X[(long long)s_row[e] * ldx + d] : (T)0;
                 }
 #pragma unroll
@@ -492,6 +494,85 @@ __device__ void cta_select2_raw(Src src, long long r0, long long r1, unsigned in
 }
 
 
+constexpr int MN_LIN_BINS = 2048;  // linear bins of the one-pass selection
+constexpr int MN_LIN_CAP = 512;    // most values its two target bins may hold
+// CTA-level (256 threads) selection of the ranks r0 <= r1 among the values of `src` (no NaN), all of which lie in
+// the finite interval [vlo, vhi], vlo < vhi.  ONE histogram pass over linear bins -- the values of a narrow bracket,
+// or of a smooth sample, spread evenly over them: no hot bins, whereas the leading digits of a radix pass put
+// thousands of values on a handful of shared-memory counters --, a scan, one pass that collects the (at most two)
+// target bins, exact ranks inside them by counting.  Returns false (for every thread) when the target bins hold more
+// than MN_LIN_CAP values -- a plateau of ties: the caller falls back to the radix select.
+template <typename T, typename Src>
+__device__ bool cta_select2_linear(Src src, long long r0, long long r1, T vlo, T vhi, unsigned int *hist /*[BINS]*/,
+                                   T *coll /*[CAP + 2]*/, unsigned int *sh /*[16]*/, T &out0, T &out1)
+{
+    const T scale = (T)MN_LIN_BINS / (vhi - vlo);
+    auto bin = [&](T x) -> int {
+        const int b = (int)((x - vlo) * scale);  // monotone in x: equal values share a bin, bins order like the values
+        return b < 0 ? 0 : (b >= MN_LIN_BINS ? MN_LIN_BINS - 1 : b);
+    };
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    for (int b = tid; b < MN_LIN_BINS; b += 256) hist[b] = 0u;
+    if (tid == 0) sh[4] = 0u;
+    __syncthreads();
+    src([&](T x) { red_shared_inc(&hist[bin(x)]); });
+    __syncthreads();
+    {   // thread t owns the bins [8t, 8t + 8): CTA-wide exclusive scan, then the two ranks' bins
+        unsigned c[8], mine = 0;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) { c[q] = hist[8 * tid + q]; mine += c[q]; }
+        unsigned incl = mine;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const unsigned v = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += v;
+        }
+        if (lane == 31) sh[8 + warp] = incl;
+        __syncthreads();
+        unsigned base = 0;
+        for (int w = 0; w < warp; ++w) base += sh[8 + w];
+        const unsigned excl = base + incl - mine;
+#pragma unroll
+        for (int which = 0; which < 2; ++which) {
+            const unsigned r = (unsigned)(which ? r1 : r0);
+            if (r >= excl && r < excl + mine) {
+                unsigned run = excl;
+#pragma unroll
+                for (int q = 0; q < 8; ++q) {
+                    if (r >= run && r < run + c[q]) { sh[2 * which] = 8 * tid + q; sh[2 * which + 1] = run; }
+                    run += c[q];
+                }
+            }
+        }
+    }
+    __syncthreads();
+    const int b0 = (int)sh[0], b1 = (int)sh[2];
+    const unsigned below0 = sh[1], below1 = sh[3];
+    const unsigned n0 = hist[b0], cnt = n0 + (b1 != b0 ? hist[b1] : 0u);
+    if (cnt > (unsigned)MN_LIN_CAP) return false;
+    src([&](T x) {
+        const int b = bin(x);
+        if (b == b0 || b == b1) coll[atomicAdd(&sh[4], 1u)] = x;
+    });
+    __syncthreads();
+    const unsigned q0 = (unsigned)r0 - below0, q1 = b1 == b0 ? (unsigned)r1 - below0 : n0 + ((unsigned)r1 - below1);
+    for (unsigned i = tid; i < cnt; i += 256) {
+        const T xi = coll[i];
+        unsigned rank = 0;
+        for (unsigned j = 0; j < cnt; ++j) {
+            const T xj = coll[j];
+            rank += (xj < xi || (xj == xi && j < i)) ? 1u : 0u;
+        }
+        if (rank == q0) coll[MN_LIN_CAP] = xi;
+        if (rank == q1) coll[MN_LIN_CAP + 1] = xi;
+    }
+    __syncthreads();
+    out0 = coll[MN_LIN_CAP];
+    out1 = coll[MN_LIN_CAP + 1];
+    __syncthreads();
+    return true;
+}
+
 // one CTA per (type, dim): pivots lo <= hi bracketing the median, from the type's sample rows
 template <typename T>
 __global__ void __launch_bounds__(256)
@@ -502,6 +583,8 @@ mn_pivot_kernel(int D, MnWs<T> ws)
     constexpr int BITS = sizeof(Key) * 8;
     __shared__ unsigned int hist[512];
     __shared__ long long sh[4];
+    __shared__ unsigned int lhist[MN_LIN_BINS], lsh[16];
+    __shared__ T lcoll[MN_LIN_CAP + 2], red_mn[8], red_mx[8];
     extern __shared__ __align__(16) unsigned char pv_raw[];
     T *vals = reinterpret_cast<T *>(pv_raw);  // MN_MCAP
     const int kd = blockIdx.x;
@@ -513,16 +596,48 @@ mn_pivot_kernel(int D, MnWs<T> ws)
         const int delta = (int)ceil(0.5 * MED_SIGMAS * sqrt((double)ns)) + 1;
         const int jlo = (ns - 1) / 2 - delta, jhi = ns / 2 + delta;
         if (jlo > 0 && jhi < ns - 1) {
-            const T *col = ws.samp + ws.samp_off[k] * D + (size_t)d * scp;
-            for (int i = threadIdx.x; i < ns; i += 256) vals[i] = col[i];
+            const T *col = ws.samp + ws.samp_off[k] * D + d;  // column d of the type's row-major sample block
+            for (int i = threadIdx.x; i < ns; i += 256) vals[i] = col[(size_t)i * D];
+            __syncthreads();
+            // valid count and range of the sample column (NaN samples sort last, as in np.sort)
+            T mn = Inf<T>::pos(), mx = -Inf<T>::pos();
+            unsigned mv = 0;
+            for (int i = threadIdx.x; i < ns; i += 256) {
+                const T x = vals[i];
+                if (x == x) { mn = x < mn ? x : mn; mx = x > mx ? x : mx; ++mv; }
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                const T a = __shfl_xor_sync(0xffffffffu, mn, o), b = __shfl_xor_sync(0xffffffffu, mx, o);
+                mn = a < mn ? a : mn;
+                mx = b > mx ? b : mx;
+                mv += __shfl_xor_sync(0xffffffffu, mv, o);
+            }
+            if ((threadIdx.x & 31) == 0) { red_mn[threadIdx.x >> 5] = mn; red_mx[threadIdx.x >> 5] = mx; lsh[8 + (threadIdx.x >> 5)] = mv; }
+            __syncthreads();
+            int m = 0;
+            for (int w = 0; w < 8; ++w) {
+                mn = red_mn[w] < mn ? red_mn[w] : mn;
+                mx = red_mx[w] > mx ? red_mx[w] : mx;
+                m += (int)lsh[8 + w];
+            }
             __syncthreads();
             auto smp = [&](auto f) {
-                for (int i = threadIdx.x; i < ns; i += 256) f(vals[i]);
+                for (int i = threadIdx.x; i < ns; i += 256) {
+                    const T x = vals[i];
+                    if (x == x) f(x);
+                }
             };
-            // NaN samples carry the largest key, i.e. they sort last, as in np.sort
-            cta_select2_raw<T>(smp, jlo, jhi, hist, sh, (Key)0, BITS - 8, lo, hi);
-            if (hi != hi) hi = Inf<T>::pos();
-            if (lo != lo) lo = -Inf<T>::pos();
+            if (jhi < m) {  // both ranks fall on valid samples; otherwise the bracket stays open (hi = +inf)
+                bool done = false;
+                if (mn == mx) { lo = hi = mn; done = true; }
+                else if (mx - mn < Inf<T>::pos())
+                    done = cta_select2_linear<T>(smp, jlo, jhi, mn, mx, lhist, lcoll, lsh, lo, hi);
+                if (!done) cta_select2_raw<T>(smp, jlo, jhi, hist, sh, (Key)0, BITS - 8, lo, hi);
+            } else if (jlo < m) {
+                T dummy;
+                cta_select2_raw<T>(smp, jlo, jlo, hist, sh, (Key)0, BITS - 8, lo, dummy);
+            }
         }
     }
     if (threadIdx.x == 0) {
@@ -633,7 +748,7 @@ mn_stream_run_kernel(const T *__restrict__ X, long long n, int D, long long ldx,
 {
     constexpr int B = MnRun<T>::B, U = MnRun<T>::U, NT = MN_RUN_THREADS;
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    T *buf = reinterpret_cast<T *>(smem_raw);                                   // [B][NT]
+    T *buf = reinterpret_cast<T *>(smem_raw);                                   // [B][NT] lane-private candidate buffers
     unsigned int *s_off = reinterpret_cast<unsigned int *>(buf + (size_t)B * NT);  // [K + 1] first sorted slot of a type
     unsigned int *s_pos = s_off + K + 1;                                        // [K] counts, then scatter cursors
     unsigned int *s_eoff = s_pos + K;                                           // [K + 1] first item-table entry of a type
@@ -724,6 +839,9 @@ mn_stream_run_kernel(const T *__restrict__ X, long long n, int D, long long ldx,
             unsigned below = 0, ties = 0, nb = 0;
             T *mybuf = buf + tid;
 
+            // append the lane's buffer to its list: one atomic reserves the space.  (A warp-cooperative variant -- one
+            // list per store instruction, lane j = entry j, 1-2 sectors instead of 32 per instruction -- measured slower:
+            // 414 vs 392 us at C3; the 32 shuffles and ballots cost more than the sector traffic they save.)
             auto flush_all = [&]() {
                 if (active && nb) {
                     const unsigned pos = atomicAdd(&ws.ncand[(size_t)rep * KD + kd], nb);
@@ -809,16 +927,17 @@ mn_stream_run_kernel(const T *__restrict__ X, long long n, int D, long long ldx,
 template <typename T>
 __global__ void __launch_bounds__(MN_FIN_THREADS)
 mn_finish_kernel(const T *__restrict__ X, long long n, int D, long long ldx, const int *__restrict__ code,
-                 MnWs<T> ws, T *__restrict__ cent, double *__restrict__ cent64)
+                 MnWs<T> ws, int STAGE, T *__restrict__ cent, double *__restrict__ cent64)
 {
     using KO = KeyOf<T>;
     using Key = typename KO::type;
     constexpr int BITS = sizeof(Key) * 8;
-    constexpr int STAGE = MN_STAGE_BYTES / (int)sizeof(T);
     extern __shared__ __align__(16) unsigned char smem_raw[];
     T *s_stage = reinterpret_cast<T *>(smem_raw);
     __shared__ unsigned int hist[512];
     __shared__ long long sh[4];
+    __shared__ unsigned int lhist[MN_LIN_BINS], lsh[16];
+    __shared__ T lcoll[MN_LIN_CAP + 2];
     __shared__ unsigned long long s_nan, s_valid;
     const int kd = blockIdx.x;
     const int k = kd / D, d = kd - k * D;
@@ -851,20 +970,33 @@ mn_finish_kernel(const T *__restrict__ X, long long n, int D, long long ldx, con
     const T lo = ws.piv[2 * kd], hi = ws.piv[2 * kd + 1];
     const long long ties = lo == hi ? tie_cnt : 0;
     const bool staged = !overflow && nlist <= STAGE;
-    // every list element, NaN included (warp w walks the replicas w, w + 8, ...)
+    // every list element, NaN included: warp w walks the replicas w, w + 8, w + 16, w + 24 TOGETHER, sixteen
+    // independent loads in flight per lane (one replica after the other made this the longest part of the kernel:
+    // a dozen dependent round trips to L2 per CTA)
     auto lst_raw = [&](auto f) {
         const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-        for (int r = warp; r < MN_REP; r += MN_FIN_THREADS / 32) {
-            const unsigned o = s_roff[r], c = s_roff[r + 1] - o;
-            const T *src = cl + (size_t)r * rstride;
-            for (unsigned i0 = lane; i0 < c; i0 += 128) {  // four independent loads in flight per lane
-                T v[4];
+        constexpr int NQ = MN_REP / (MN_FIN_THREADS / 32);
+        unsigned o[NQ], c[NQ], cm = 0;
+        const T *src[NQ];
 #pragma unroll
-                for (int u = 0; u < 4; ++u) v[u] = i0 + 32 * u < c ? src[i0 + 32 * u] : (T)0;
+        for (int q = 0; q < NQ; ++q) {
+            const int r = warp + q * (MN_FIN_THREADS / 32);
+            o[q] = s_roff[r];
+            c[q] = s_roff[r + 1] - o[q];
+            src[q] = cl + (size_t)r * rstride;
+            cm = c[q] > cm ? c[q] : cm;
+        }
+        for (unsigned i0 = lane; i0 < cm; i0 += 128) {
+            T v[NQ][4];
+#pragma unroll
+            for (int q = 0; q < NQ; ++q)
+#pragma unroll
+                for (int u = 0; u < 4; ++u) v[q][u] = i0 + 32 * u < c[q] ? src[q][i0 + 32 * u] : (T)0;
+#pragma unroll
+            for (int q = 0; q < NQ; ++q)
 #pragma unroll
                 for (int u = 0; u < 4; ++u)
-                    if (i0 + 32 * u < c) f(o + i0 + 32 * u, v[u]);
-            }
+                    if (i0 + 32 * u < c[q]) f(o[q] + i0 + 32 * u, v[q][u]);
         }
     };
     unsigned my_nan = 0;
@@ -938,16 +1070,22 @@ mn_finish_kernel(const T *__restrict__ X, long long n, int D, long long ldx, con
             T m0 = lo, m1 = lo;
             if (g0 == 2 || g1 == 2) {
                 auto lst = [&](auto f) { lst_all([&](T x) { if (x == x) f(x); }); };
-                // every orderable list element lies in [lo, hi]: the digits above the first one in
-                // which key(lo) and key(hi) differ are common to all of them
-                Key prefix = 0;
-                int first = BITS - 8;
-                if (lo > -Inf<T>::pos() && hi < Inf<T>::pos()) {
-                    const Key kl = KO::key(lo), kh = KO::key(hi);
-                    while (first > 0 && (kl >> first) == (kh >> first)) first -= 8;
-                    if (first < BITS - 8) prefix = (Key)((kl >> (first + 8)) << (first + 8));
+                const long long s0 = g0 == 2 ? j0 : (g1 == 2 ? j1 : 0), s1 = g1 == 2 ? j1 : s0;  // s0 <= s1
+                bool done = false;
+                const bool finite = lo > -Inf<T>::pos() && hi < Inf<T>::pos();
+                // every orderable list element lies in [lo, hi]: linear bins over the bracket
+                if (finite && lo < hi) done = cta_select2_linear<T>(lst, s0, s1, lo, hi, lhist, lcoll, lsh, m0, m1);
+                if (!done) {
+                    // radix select; the digits above the first one in which key(lo) and key(hi) differ are common
+                    Key prefix = 0;
+                    int first = BITS - 8;
+                    if (finite) {
+                        const Key kl = KO::key(lo), kh = KO::key(hi);
+                        while (first > 0 && (kl >> first) == (kh >> first)) first -= 8;
+                        if (first < BITS - 8) prefix = (Key)((kl >> (first + 8)) << (first + 8));
+                    }
+                    cta_select2_raw<T>(lst, s0, s1, hist, sh, prefix, first, m0, m1);
                 }
-                cta_select2_raw<T>(lst, g0 == 2 ? j0 : 0, g1 == 2 ? j1 : 0, hist, sh, prefix, first, m0, m1);
             }
             v0 = g0 == 1 ? lo : m0;
             v1 = g1 == 1 ? lo : m1;
@@ -1070,8 +1208,20 @@ static int median_run_stream(const T *X, long long n, int D, long long ldx, cons
         mn_stream_kernel<T><<<(unsigned)ctas, MN_THREADS, smem, st>>>(X, n, D, ldx, code, K, ws);
         PILOT_LAUNCH_CHECK();
     }
-    PILOT_CUDA(cudaFuncSetAttribute(mn_finish_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, MN_STAGE_BYTES));
-    mn_finish_kernel<T><<<(unsigned)kd, MN_FIN_THREADS, MN_STAGE_BYTES, st>>>(X, n, D, ldx, code, ws, cent, cent64);
+    {
+        // stage size from the expected list length: bracket fraction 5.5 / sqrt(sample) of an average type, + 50 %;
+        // a longer list is selected from global memory instead (L2 resident), a shorter stage lets more CTAs share an SM
+        const double nk = (double)n / K;
+        double ns = nk / 16;
+        ns = ns < MN_SAMPLE_MIN ? MN_SAMPLE_MIN : (ns > MN_SAMPLE_MAX ? MN_SAMPLE_MAX : ns);
+        if (ns > nk) ns = nk > 1 ? nk : 1;
+        size_t bytes = (size_t)(1.5 * MED_SIGMAS / sqrt(ns) * nk) * sizeof(T);
+        bytes = bytes < MN_STAGE_MIN ? MN_STAGE_MIN : (bytes > MN_STAGE_MAX ? MN_STAGE_MAX : bytes);
+        bytes = (bytes + 1023) & ~(size_t)1023;
+        PILOT_CUDA(cudaFuncSetAttribute(mn_finish_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, MN_STAGE_MAX));
+        mn_finish_kernel<T><<<(unsigned)kd, MN_FIN_THREADS, bytes, st>>>(X, n, D, ldx, code, ws, (int)(bytes / sizeof(T)),
+                                                                         cent, cent64);
+    }
     PILOT_LAUNCH_CHECK();
     return 0;
 }

@@ -169,3 +169,31 @@ def test_object_column_factorize_fast_path_equals_pandas():
     assert np.array_equal(got[0], want_codes) and list(got[1]) == list(want_labels) and got[0][5] == -1
     codes, labels = tl._raw_codes(shared.rename("cell_type"))
     assert codes.dtype == np.int32 and list(labels) == list(pd.factorize(shared, sort=False)[1])
+
+
+def test_factorisation_cache_hits_only_on_identical_object_columns():
+    """Object label columns are factorised once; a later call with the same objects in every cell reuses the
+    result, any changed cell misses (tl._factor_cache_get validates every pointer)."""
+    rng = np.random.default_rng(5)
+    n = 60_000
+    base = pd.Series(rng.integers(0, 25, n)).astype(str).astype(object)     # every cell its own str object
+    df = pd.DataFrame({"a": base})
+    tl._factor_cache.clear()
+
+    def codes_of(frame):
+        annot = frame[["a"]].reset_index(drop=True)
+        return tl._raw_codes(annot["a"])
+
+    c0, l0 = codes_of(df)
+    assert len(tl._factor_cache) == 1
+    c1, l1 = codes_of(df)                                                      # same objects: served from the cache
+    assert c1 is c0 and list(l1) == list(l0)
+    wc, wl = pd.factorize(df["a"], sort=False)
+    assert np.array_equal(c0, wc) and list(l0) == list(wl)
+    df.loc[n // 3, "a"] = "other"                                              # one cell changes: exact validation misses
+    c2, l2 = codes_of(df)
+    wc, wl = pd.factorize(df["a"], sort=False)
+    assert np.array_equal(c2, wc) and list(l2) == list(wl) and "other" in list(l2)
+    for i in range(6):                                                         # bounded
+        codes_of(pd.DataFrame({"a": pd.Series(rng.integers(0, 5, n)).astype(str).astype(object)}))
+    assert len(tl._factor_cache) <= tl._FACTOR_CACHE_MAX
