@@ -144,6 +144,44 @@ def _factor_cache_put(col: pd.Series, codes, labels) -> None:
     _factor_cache[key] = (vals.copy(), codes, labels)
 
 
+_host_lib = {"lib": None, "tried": False}
+
+
+def _host_helper():
+    """libpilot_host.so (csrc/host_ingest.c), loaded with the GIL held; None when it has not been built."""
+    if not _host_lib["tried"]:
+        _host_lib["tried"] = True
+        import ctypes
+        path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "csrc", "libpilot_host.so")
+        if os.path.isfile(path):
+            lib = ctypes.PyDLL(path)
+            lib.pilot_factorize_str.restype = ctypes.c_int64
+            lib.pilot_factorize_str.argtypes = [ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p, ctypes.c_void_p,
+                                                ctypes.c_int64]
+            _host_lib["lib"] = lib
+    return _host_lib["lib"]
+
+
+def _factorize_str_native(vals: np.ndarray):
+    """(codes int32, labels object ndarray) of a contiguous object array of str, in order of first appearance, by
+    the C helper; None when it does not apply (helper missing, non-str cells, > 2^20 labels)."""
+    import ctypes
+    lib = _host_helper()
+    n = len(vals)
+    if lib is None or n == 0:
+        return None
+    max_unique = min(n, 1 << 20)
+    codes = np.empty(n, dtype=np.int32)
+    uniq = np.zeros(max_unique, dtype=np.uintp)
+    m = lib.pilot_factorize_str(vals.ctypes.data, n, codes.ctypes.data, uniq.ctypes.data, max_unique)
+    if m < 0:
+        return None
+    labels = np.empty(m, dtype=object)
+    for i in range(m):
+        labels[i] = ctypes.cast(int(uniq[i]), ctypes.py_object).value   # borrowed from `vals`, which is alive
+    return codes, labels
+
+
 def _factorize_object_column(col: pd.Series):
     """pd.factorize(col, sort=False) for an object column that holds few distinct Python objects -- the usual
     case for label columns (a million references to a few dozen str objects).  Hashing Python objects costs
@@ -155,6 +193,9 @@ def _factorize_object_column(col: pd.Series):
     n = len(vals)
     if n < 50_000 or vals.dtype != object or not vals.flags.c_contiguous:
         return None
+    native = _factorize_str_native(vals)
+    if native is not None:
+        return native
     ptrs = np.ctypeslib.as_array((ctypes.c_ssize_t * n).from_address(vals.ctypes.data))
     pcodes, puniq = pd.factorize(ptrs, sort=False)  # by identity, in order of first appearance
     if len(puniq) > max(4096, n // 16):

@@ -161,7 +161,12 @@ def test_object_column_factorize_fast_path_equals_pandas():
         assert got is not None
         want_codes, want_labels = pd.factorize(col, sort=False)
         assert np.array_equal(got[0], want_codes) and list(got[1]) == list(want_labels)
-    assert tl._factorize_object_column(dup) is None            # no gain: falls back to pd.factorize
+    got = tl._factorize_object_column(dup)                     # every cell its own object: the C helper, or None
+    if tl._host_helper() is None:
+        assert got is None                                     # (pointer-first has no gain: pd.factorize is used)
+    else:
+        want_codes, want_labels = pd.factorize(dup, sort=False)
+        assert np.array_equal(got[0], want_codes) and list(got[1]) == list(want_labels)
     withnan = shared.copy()
     withnan.iloc[5] = np.nan
     got = tl._factorize_object_column(withnan)
@@ -197,3 +202,29 @@ def test_factorisation_cache_hits_only_on_identical_object_columns():
     for i in range(6):                                                         # bounded
         codes_of(pd.DataFrame({"a": pd.Series(rng.integers(0, 5, n)).astype(str).astype(object)}))
     assert len(tl._factor_cache) <= tl._FACTOR_CACHE_MAX
+
+
+def test_native_str_factorisation_equals_pandas():
+    """csrc/host_ingest.c (libpilot_host.so): codes and labels in order of first appearance like
+    pd.factorize(sort=False); ASCII, non-ASCII, empty strings, equal values in different objects, runs of one
+    object; non-str cells make it step aside for pandas."""
+    if tl._host_helper() is None:
+        pytest.skip("libpilot_host.so not built")
+    rng = np.random.default_rng(9)
+    n = 70_000
+    pools = [np.array([f"type {i}" for i in range(37)], dtype=object),
+             np.array(["α-cell", "β", "naïve T", "", "x", "naive T", "日本"], dtype=object)]
+    for pool in pools:
+        shared = pool[rng.integers(0, len(pool), n)]                       # few objects, many references
+        distinct = pd.Series(shared).astype(str).astype(object).to_numpy()  # every cell its own object
+        runs = np.repeat(pool, n // len(pool) + 1)[:n]                      # long runs of one pointer
+        for vals in (shared, distinct, runs):
+            got = tl._factorize_str_native(np.ascontiguousarray(vals))
+            assert got is not None
+            wc, wl = pd.factorize(vals, sort=False)
+            assert np.array_equal(got[0], wc) and list(got[1]) == list(wl)
+    mixed = pools[0][rng.integers(0, 37, n)].copy()
+    mixed[n // 2] = None
+    assert tl._factorize_str_native(mixed) is None
+    mixed[n // 2] = 3.5
+    assert tl._factorize_str_native(mixed) is None
