@@ -41,6 +41,11 @@ extern "C" {
 #define PILOT_METRIC_CITYBLOCK   3
 #define PILOT_METRIC_CHEBYSHEV   4
 #define PILOT_METRIC_CORRELATION 5
+#define PILOT_METRIC_BRAYCURTIS  6
+#define PILOT_METRIC_CANBERRA    7
+#define PILOT_METRIC_MINKOWSKI   8   /* SciPy's default p = 2 */
+#define PILOT_METRIC_SEUCLIDEAN  9   /* V = var(centroids, axis=0, ddof=1), SciPy's default */
+#define PILOT_METRIC_HAMMING     10
 
 /* how a linear problem index g maps to a sample pair (i, j) */
 #define PILOT_PAIRS_FULL  0   /* g = i*S + j, all S*S ordered pairs incl. diagonal     */
@@ -165,7 +170,9 @@ int pilot_sinkhorn_pairs(const double *props, int S, int K, const double *cost,
  * Trajectory.py:507-511 (b is rescaled to a's mass as emd2 does).
  * out[l] = optimal transport cost of local problem l; status/pivots may be NULL.
  * precision: PILOT_F64 (costs, flows and potentials in double: within 1e-9 of
- * POT) or PILOT_F32 (the same solver on float: within 1e-4).  1 <= K <= 64.
+ * POT) or PILOT_F32 (the same solver on float: within 1e-4).  1 <= K <= 256:
+ * up to 64 types the bit-mask solver (emd.cu), 65..256 a general network simplex
+ * (emd_general.cu, FP64 whatever the precision) -- ot.emd2 itself has no limit.
  */
 int pilot_emd_pairs(const double *props, int S, int K, const double *cost,
                     int64_t max_pivots, const pilot_pair_range *range,

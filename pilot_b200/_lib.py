@@ -19,7 +19,9 @@ METRICS = {"cosine": 0, "cos": 0, "euclidean": 1, "euclid": 1, "eu": 1, "e": 1, 
            "sqeuclidean": 2, "sqe": 2, "sqeuclid": 2,
            "cityblock": 3, "cblock": 3, "cb": 3, "c": 3, "manhattan": 3, "taxicab": 3, "l1": 3,
            "chebyshev": 4, "chebychev": 4, "chebyshev": 4, "cheby": 4, "cheb": 4, "ch": 4, "linf": 4,
-           "correlation": 5, "co": 5}
+           "correlation": 5, "co": 5,
+           "braycurtis": 6, "canberra": 7, "minkowski": 8, "mi": 8, "m": 8, "pnorm": 8,
+           "seuclidean": 9, "se": 9, "s": 9, "hamming": 10, "hamm": 10, "ha": 10, "h": 10, "matching": 10}
 PAIRS_FULL, PAIRS_UPPER = 0, 1
 PRECISIONS = {"f64": F64, "fp64": F64, "float64": F64, "double": F64,
               "f32": F32, "fp32": F32, "float32": F32, "single": F32}

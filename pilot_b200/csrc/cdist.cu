@@ -42,6 +42,43 @@ __global__ void cdist_pair_kernel(const double *__restrict__ C, int K, int D, in
     const double *u = C + (long long)i * D, *v = C + (long long)j * D;
     double acc = 0.0, r;
     switch (metric) {
+    case PILOT_METRIC_BRAYCURTIS: {
+        double den = 0.0;
+        for (int d = 0; d < D; ++d) {
+            acc = __dadd_rn(acc, fabs(__dsub_rn(u[d], v[d])));
+            den = __dadd_rn(den, fabs(__dadd_rn(u[d], v[d])));
+        }
+        r = __ddiv_rn(acc, den);
+        break;
+    }
+    case PILOT_METRIC_CANBERRA:
+        for (int d = 0; d < D; ++d) {
+            const double num = fabs(__dsub_rn(u[d], v[d])), den = __dadd_rn(fabs(u[d]), fabs(v[d]));
+            if (den != 0.0) acc = __dadd_rn(acc, __ddiv_rn(num, den));  // SciPy: a 0 / 0 term contributes 0
+        }
+        r = acc;
+        break;
+    case PILOT_METRIC_SEUCLIDEAN:
+        // V = var(centroids, axis=0, ddof=1), SciPy's default for pdist(..., 'seuclidean')
+        for (int d = 0; d < D; ++d) {
+            double s = 0.0;
+            for (int k = 0; k < K; ++k) s = __dadd_rn(s, C[(long long)k * D + d]);
+            const double mean = __ddiv_rn(s, (double)K);
+            double ss = 0.0;
+            for (int k = 0; k < K; ++k) {
+                const double e = __dsub_rn(C[(long long)k * D + d], mean);
+                ss = __dadd_rn(ss, __dmul_rn(e, e));
+            }
+            const double var = __ddiv_rn(ss, (double)(K - 1));
+            const double df = __dsub_rn(u[d], v[d]);
+            acc = __dadd_rn(acc, __ddiv_rn(__dmul_rn(df, df), var));
+        }
+        r = sqrt(acc);
+        break;
+    case PILOT_METRIC_HAMMING:
+        for (int d = 0; d < D; ++d) acc += u[d] != v[d] ? 1.0 : 0.0;
+        r = __ddiv_rn(acc, (double)D);
+        break;
     case PILOT_METRIC_COSINE:
     case PILOT_METRIC_CORRELATION: {
         const double mu = means[i], mv = means[j];
@@ -53,12 +90,13 @@ __global__ void cdist_pair_kernel(const double *__restrict__ C, int K, int D, in
         break;
     }
     case PILOT_METRIC_EUCLIDEAN:
+    case PILOT_METRIC_MINKOWSKI:  // SciPy's default p = 2 takes its Euclidean routine (bit-identical results)
     case PILOT_METRIC_SQEUCLIDEAN:
         for (int d = 0; d < D; ++d) {
             const double df = __dsub_rn(u[d], v[d]);
             acc = __dadd_rn(acc, __dmul_rn(df, df));
         }
-        r = metric == PILOT_METRIC_EUCLIDEAN ? sqrt(acc) : acc;
+        r = metric == PILOT_METRIC_SQEUCLIDEAN ? acc : sqrt(acc);
         break;
     case PILOT_METRIC_CITYBLOCK:
         for (int d = 0; d < D; ++d) acc = __dadd_rn(acc, fabs(__dsub_rn(u[d], v[d])));
@@ -111,7 +149,7 @@ extern "C" int pilot_cdist(const double *centroids_f64, int K, int D, int metric
 {
     using namespace pilot;
     PILOT_CHECK_ARG(K >= 1 && D >= 1 && centroids_f64 && cost, "pilot_cdist: bad argument");
-    PILOT_CHECK_ARG(metric >= PILOT_METRIC_COSINE && metric <= PILOT_METRIC_CORRELATION,
+    PILOT_CHECK_ARG(metric >= PILOT_METRIC_COSINE && metric <= PILOT_METRIC_HAMMING,
                     "pilot_cdist: unsupported metric id %d", metric);
     PILOT_CHECK_ARG(K <= 4096, "pilot_cdist: K=%d too large", K);
     PILOT_CHECK_ARG(cost_norm != nullptr, "pilot_cdist: cost_norm is required (it doubles as scratch)");

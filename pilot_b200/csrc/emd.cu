@@ -671,6 +671,9 @@ static int emd_launch(const double *props, int K, const double *cost, const Pair
     return 0;
 }
 
+int emd_general_launch(const double *props, int K, const double *cost, const PairMap &pm, long long max_pivots,
+                       double *out, int *status, int *pivots, void *workspace, cudaStream_t st);
+
 size_t emd_ws_bytes(int K)
 {
     (void)K;
@@ -686,7 +689,7 @@ extern "C" int pilot_emd_pairs(const double *props, int S, int K, const double *
     using namespace pilot;
     PILOT_CHECK_ARG(props && cost && out && workspace, "pilot_emd_pairs: NULL pointer");
     PILOT_CHECK_ARG(S >= 1, "pilot_emd_pairs: S=%d", S);
-    PILOT_CHECK_ARG(K >= 1 && K <= 64, "pilot_emd_pairs: K=%d outside the supported range [1, 64]", K);
+    PILOT_CHECK_ARG(K >= 1 && K <= 256, "pilot_emd_pairs: K=%d outside the supported range [1, 256]", K);
     PILOT_CHECK_ARG(precision == PILOT_F64 || precision == PILOT_F32, "pilot_emd_pairs: precision=%d", precision);
     PILOT_CHECK_ARG(workspace_bytes >= emd_ws_bytes(K), "pilot_emd_pairs: workspace too small");
     PairMap pm;
@@ -696,6 +699,8 @@ extern "C" int pilot_emd_pairs(const double *props, int S, int K, const double *
     if (max_pivots <= 0) max_pivots = 100000;  // POT numItermax default
     cudaStream_t st = (cudaStream_t)stream;
     PILOT_CUDA(cudaMemsetAsync(workspace, 0, 256, st));
+    if (K > 64)  // beyond the bit-mask solver: general network simplex (emd_general.cu), FP64 whatever the precision
+        return emd_general_launch(props, K, cost, pm, max_pivots, out, status, pivots, workspace, st);
     if (precision == PILOT_F64) {
         if (K <= 32) return emd_launch<1, double>(props, K, cost, pm, max_pivots, out, status, pivots, workspace, st);
         return emd_launch<2, double>(props, K, cost, pm, max_pivots, out, status, pivots, workspace, st);

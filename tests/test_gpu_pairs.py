@@ -88,6 +88,44 @@ def test_emd_degenerate_inputs():
     np.testing.assert_allclose(got, want, rtol=EMD_RTOL, atol=1e-14)
 
 
+@pytest.mark.parametrize("K,S", [(65, 10), (100, 10), (128, 8), (200, 6), (256, 5)])
+def test_emd_more_than_64_types_general_kernel(K, S):
+    """ot.emd2 has no limit on the number of cell types; beyond the bit-mask solver (K <= 64) the general network
+    simplex of emd_general.cu takes over (Trajectory.py:511).  Same optimum as the oracle, zero diagonal."""
+    P, M = synth.make_pairs(S, K, seed=900 + K)
+    P[1, : K // 3] = 0.0
+    P[1] /= P[1].sum()                                 # zero masses stay in the problem with supply 0
+    P[2] = P[0]                                        # an identical pair
+    rng = ops.make_range(S * S, _lib.PAIRS_FULL)
+    out, status, piv = ops.emd_pairs(dev(P), dev(M), rng, want_info=True)
+    got = out.cpu().numpy().reshape(S, S)
+    want = oracle_emd_matrix(P, M)
+    assert (status.cpu().numpy() == 0).all()
+    np.testing.assert_allclose(got, want, rtol=EMD_RTOL, atol=1e-14)
+    assert np.abs(np.diag(got)).max() <= 1e-14 and abs(got[0, 2]) <= 1e-14
+    assert piv.cpu().numpy().max() > 0
+    # the driver above it: symmetric cost -> upper triangle + mirror, as for K <= 64
+    full = pairs.all_pairs(dev(P), dev(M), "unreg").cpu().numpy()
+    np.testing.assert_allclose(full, want, rtol=EMD_RTOL, atol=1e-14)
+
+
+def test_emd_general_kernel_agrees_with_the_bitmask_kernel_and_limits():
+    """K = 64 padded with an empty 65th type goes through the general kernel and must reproduce the K = 64 result of
+    the bit-mask kernel; more than 256 types raise."""
+    S, K = 12, 64
+    P, M = synth.make_pairs(S, K, seed=77)
+    rng = ops.make_range(S * S, _lib.PAIRS_FULL)
+    base = ops.emd_pairs(dev(P), dev(M), rng).cpu().numpy()
+    P65 = np.concatenate([P, np.zeros((S, 1))], axis=1)
+    M65 = np.ones((65, 65)) * 0.5
+    M65[:64, :64] = M
+    M65[64, 64] = 0.0
+    padded = ops.emd_pairs(dev(P65), dev(M65), rng).cpu().numpy()
+    np.testing.assert_allclose(padded, base, rtol=1e-12, atol=1e-15)
+    with pytest.raises(_lib.PilotLibraryError):
+        ops.emd_pairs(dev(np.full((2, 257), 1 / 257)), dev(np.zeros((257, 257))), ops.make_range(4, _lib.PAIRS_FULL))
+
+
 def test_emd_nonmetric_cost_and_counts():
     # raw counts with equal totals (normalization=False) and an asymmetric, non-zero-diagonal cost
     rng_ = np.random.default_rng(3)

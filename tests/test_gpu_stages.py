@@ -140,10 +140,15 @@ def test_centroid_median_column_form_shapes(dtype, n, K, D):
         np.testing.assert_array_equal(cent2.cpu().numpy(), want.astype(dtype))
 
 
-@pytest.mark.parametrize("metric", ["cosine", "euclidean", "sqeuclidean", "cityblock", "chebyshev", "correlation"])
+@pytest.mark.parametrize("metric", ["cosine", "euclidean", "sqeuclidean", "cityblock", "chebyshev", "correlation",
+                                    "braycurtis", "canberra", "minkowski", "seuclidean", "hamming"])
 def test_cdist_matches_scipy(metric):
     rng = np.random.default_rng(4)
     C = rng.normal(size=(37, 50))
+    if metric == "hamming":
+        C = np.round(C)                     # coordinates that actually coincide
+    if metric == "canberra":
+        C[:, 3] = 0.0                       # 0 / 0 terms contribute nothing
     cost, cost_norm, cmax = ops.cdist(dev(C), metric)
     want = ssd.squareform(ssd.pdist(C, metric))
     np.testing.assert_allclose(cost.cpu().numpy(), want, rtol=1e-12, atol=1e-14)
