@@ -575,15 +575,15 @@ __device__ bool cta_select2_linear(Src src, long long r0, long long r1, T vlo, T
 
 // one CTA per (type, dim): pivots lo <= hi bracketing the median, from the type's sample rows
 template <typename T>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 6)
 mn_pivot_kernel(int D, MnWs<T> ws)
 {
     using KO = KeyOf<T>;
     using Key = typename KO::type;
     constexpr int BITS = sizeof(Key) * 8;
-    __shared__ unsigned int hist[512];
     __shared__ long long sh[4];
     __shared__ unsigned int lhist[MN_LIN_BINS], lsh[16];
+    unsigned int *hist = lhist;  // the radix fallback's 512 counters: never live together with the linear bins
     __shared__ T lcoll[MN_LIN_CAP + 2], red_mn[8], red_mx[8];
     extern __shared__ __align__(16) unsigned char pv_raw[];
     T *vals = reinterpret_cast<T *>(pv_raw);  // MN_MCAP
@@ -925,7 +925,7 @@ mn_stream_run_kernel(const T *__restrict__ X, long long n, int D, long long ldx,
 // one CTA per (type, dim): rank bookkeeping (below / tie plateau / list / above), NaN count and selection inside
 // the list, exact fallback over the type's own rows when the bracket missed or the list overflowed
 template <typename T>
-__global__ void __launch_bounds__(MN_FIN_THREADS)
+__global__ void __launch_bounds__(MN_FIN_THREADS, 5)
 mn_finish_kernel(const T *__restrict__ X, long long n, int D, long long ldx, const int *__restrict__ code,
                  MnWs<T> ws, int STAGE, T *__restrict__ cent, double *__restrict__ cent64)
 {
@@ -934,9 +934,9 @@ mn_finish_kernel(const T *__restrict__ X, long long n, int D, long long ldx, con
     constexpr int BITS = sizeof(Key) * 8;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     T *s_stage = reinterpret_cast<T *>(smem_raw);
-    __shared__ unsigned int hist[512];
     __shared__ long long sh[4];
     __shared__ unsigned int lhist[MN_LIN_BINS], lsh[16];
+    unsigned int *hist = lhist;  // the radix paths' 512 counters: never live together with the linear bins
     __shared__ T lcoll[MN_LIN_CAP + 2];
     __shared__ unsigned long long s_nan, s_valid;
     const int kd = blockIdx.x;
@@ -1209,13 +1209,13 @@ static int median_run_stream(const T *X, long long n, int D, long long ldx, cons
         PILOT_LAUNCH_CHECK();
     }
     {
-        // stage size from the expected list length: bracket fraction 5.5 / sqrt(sample) of an average type, + 50 %;
+        // stage size from the expected list length: bracket fraction 5.5 / sqrt(sample) of an average type, + 25 %;
         // a longer list is selected from global memory instead (L2 resident), a shorter stage lets more CTAs share an SM
         const double nk = (double)n / K;
         double ns = nk / 16;
         ns = ns < MN_SAMPLE_MIN ? MN_SAMPLE_MIN : (ns > MN_SAMPLE_MAX ? MN_SAMPLE_MAX : ns);
         if (ns > nk) ns = nk > 1 ? nk : 1;
-        size_t bytes = (size_t)(1.5 * MED_SIGMAS / sqrt(ns) * nk) * sizeof(T);
+        size_t bytes = (size_t)(1.25 * MED_SIGMAS / sqrt(ns) * nk) * sizeof(T);
         bytes = bytes < MN_STAGE_MIN ? MN_STAGE_MIN : (bytes > MN_STAGE_MAX ? MN_STAGE_MAX : bytes);
         bytes = (bytes + 1023) & ~(size_t)1023;
         PILOT_CUDA(cudaFuncSetAttribute(mn_finish_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, MN_STAGE_MAX));
