@@ -9,7 +9,8 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "csrc", "libpilot_b200.so")
+# PILOT_B200_LIB: another build of the same library (A/B measurements of kernel variants only)
+LIB_PATH = os.environ.get("PILOT_B200_LIB") or os.path.join(_HERE, "csrc", "libpilot_b200.so")
 
 ABI_VERSION = 2
 
