@@ -19,9 +19,7 @@
 
 namespace pilot {
 
-constexpr int EMG_MAXK = 256;
-constexpr int EMG_JMAX = EMG_MAXK / 32;  // columns per lane
-constexpr int EMG_ROWS = 4;              // rows per pricing block
+constexpr int EMG_ROWS = 4;  // rows per pricing block
 
 // per-warp state, N = 2K + 1 nodes (sources 0..K-1, sinks K..2K-1, root 2K)
 struct EmgView {

@@ -74,7 +74,7 @@ def _parse_datatype(buf: bytes, off: int = 0) -> Tuple[_Datatype, int]:
         t.dtype = np.dtype(f"<u{t.size}")
         p += 4
     elif t.cls == 5:    # opaque
-        taglen = (bits & 0xFF + 7) & ~7
+        taglen = ((bits & 0xFF) + 7) & ~7
         t.dtype = np.dtype(f"V{t.size}")
         p += taglen
     elif t.cls == 6:    # compound
@@ -707,8 +707,9 @@ def _read_array(obj: _Object, f: H5File):
         return cls((obj["data"].read(), obj["indices"].read(), obj["indptr"].read()), shape=shape)
     if enc in ("nullable-integer", "nullable-boolean"):
         vals, mask = obj["values"].read(), obj["mask"].read().astype(bool)
-        return pd.array(np.where(mask, 0, vals), dtype="Int64" if enc == "nullable-integer" else "boolean").__class__(
-            np.where(mask, 0, vals), mask)
+        if enc == "nullable-integer":
+            return pd.arrays.IntegerArray(np.where(mask, 0, vals), mask)
+        return pd.arrays.BooleanArray(np.where(mask, False, vals).astype(bool), mask)
     if enc == "dataframe" or "_index" in obj.attrs:
         return _read_dataframe(obj, f)
     return _read_mapping(obj, f)
