@@ -140,6 +140,30 @@ def test_centroid_median_column_form_shapes(dtype, n, K, D):
         np.testing.assert_array_equal(cent2.cpu().numpy(), want.astype(dtype))
 
 
+@pytest.mark.parametrize("order", ["by_type", "by_type_blocks", "one_type_dominates"])
+def test_centroid_median_sorted_inputs_stay_on_the_fast_path(order):
+    """AnnData objects are often sorted by cluster or by sample.  The run-form stream pass counting-sorts 4096-row
+    chunks: a chunk then holds one type only (one long run cut into 128-row segments), and a type's candidates come
+    from a few chunks -- the list replicas must still fill evenly (no overflow -> no exact fallback) and the result
+    stays exact."""
+    rng = np.random.default_rng(21)
+    n, K, D = 400_000, 12, 50
+    X = rng.normal(size=(n, D)).astype(np.float32)
+    code = rng.integers(0, K, size=n).astype(np.int32)
+    if order == "by_type":
+        code = np.sort(code)
+    elif order == "by_type_blocks":
+        code = np.repeat(rng.permutation(np.arange(K * 8) % K), n // (K * 8) + 1)[:n].astype(np.int32)
+    else:
+        code = np.where(rng.random(n) < 0.9, 3, code).astype(np.int32)
+    X += code[:, None].astype(np.float32)             # type-dependent location: a wrong row assignment would show
+    cent, cent64 = ops.centroid_median(dev(X), dev(code), K)
+    assert ops.median_fallbacks(K, D) == 0
+    want = np.stack([np.nanmedian(X[code == k], axis=0) for k in range(K)])
+    np.testing.assert_array_equal(cent.cpu().numpy(), want)
+    np.testing.assert_array_equal(cent64.cpu().numpy(), want.astype(np.float64))
+
+
 @pytest.mark.parametrize("metric", ["cosine", "euclidean", "sqeuclidean", "cityblock", "chebyshev", "correlation",
                                     "braycurtis", "canberra", "minkowski", "seuclidean", "hamming"])
 def test_cdist_matches_scipy(metric):
