@@ -714,7 +714,12 @@ def run_cells(args):
                                                "str object (the reference's default user input, Trajectory.py:255-263); "
                                                "ms_per_step: repeated calls on the same label objects (validated "
                                                "factorisation cache), first_call_ms: the call that factorises them"}},
-            "gpu_launches": int(launches), "stage_ms": stage_ms, "roofline": roofline, "pipe_peaks": peaks}
+            "gpu_launches": int(launches), "stage_ms": stage_ms, "roofline": roofline, "pipe_peaks": peaks,
+            # the two HBM-bound stages against the measured copy bandwidth (whole stage, all its kernels)
+            "stage_hbm": {kn: {"algorithmic_bytes": int(alg_bytes[kn]),
+                               "achieved_gbs": alg_bytes[kn] / (stage_ms[kn] * 1e-3) / 1e9,
+                               "frac": alg_bytes[kn] / (stage_ms[kn] * 1e-3) / 1e9 / hbm_peak}
+                          for kn in ("hist", "median") if kn in stage_ms}}
     if world == 1:
         rows = max(1, min(s, 2000 // s + 1))
         cb = cpu_reference_step(X, obs, reg, rows)
