@@ -15,7 +15,7 @@
 
 namespace pilot {
 
-constexpr int KNN_THREADS = 256;
+constexpr int KNN_THREADS = 1024;  // one CTA per SM (the staged row fills shared memory): all 32 warps of it
 constexpr int KNN_MAXK = 1024;
 
 __global__ void knn_sqnorm_kernel(const double *__restrict__ G, int S, double *__restrict__ sq)
@@ -45,7 +45,23 @@ knn_rows_kernel(const double *__restrict__ G, const double *__restrict__ sq, int
         return v > 0.0 ? v : 0.0;
     };
     if (STAGED) {
-        for (int j = threadIdx.x; j < S; j += blockDim.x) srow[j] = d2(j);
+        constexpr int UB = 8;  // independent loads in flight per thread
+        for (int j0 = threadIdx.x; j0 < S; j0 += UB * KNN_THREADS) {
+            double g[UB], nj[UB];
+#pragma unroll
+            for (int u = 0; u < UB; ++u) {
+                const int j = j0 + u * KNN_THREADS;
+                g[u] = j < S ? grow[j] : 0.0;
+                nj[u] = j < S ? sq[j] : 0.0;
+            }
+#pragma unroll
+            for (int u = 0; u < UB; ++u) {
+                const int j = j0 + u * KNN_THREADS;
+                if (j >= S) continue;
+                const double v = (ni + nj[u]) - 2.0 * g[u];
+                srow[j] = j == i ? 0.0 : (v > 0.0 ? v : 0.0);
+            }
+        }
         __syncthreads();
     }
     auto val = [&](int j) -> double { return STAGED ? srow[j] : d2(j); };

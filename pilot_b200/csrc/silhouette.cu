@@ -19,7 +19,7 @@
 
 namespace pilot {
 
-constexpr int SIL_THREADS = 256;
+constexpr int SIL_THREADS = 1024;  // one CTA per SM (the staged row fills shared memory): all 32 warps of it
 constexpr int SIL_MAXL = 4096;
 
 __global__ void sil_prep_kernel(const double *__restrict__ M, int S, int metric, double *__restrict__ nrm)
@@ -53,15 +53,52 @@ sil_rows_kernel(const double *__restrict__ M, const double *__restrict__ nrm, in
         const double v = (ni + nrm[j]) - 2.0 * row[j];
         return v > 0.0 ? sqrt(v) : 0.0;
     };
+    constexpr int UB = 8;  // independent loads in flight per thread: both loops are chains of L2 round trips otherwise
     if (STAGED) {
-        for (int j = threadIdx.x; j < S; j += blockDim.x) srow[j] = dist(j);
+        for (int j0 = threadIdx.x; j0 < S; j0 += UB * SIL_THREADS) {
+            double g[UB], nj[UB];
+#pragma unroll
+            for (int u = 0; u < UB; ++u) {
+                const int j = j0 + u * SIL_THREADS;
+                g[u] = j < S ? row[j] : 0.0;
+                nj[u] = (j < S && metric != PILOT_SIL_PRECOMPUTED) ? nrm[j] : 0.0;
+            }
+#pragma unroll
+            for (int u = 0; u < UB; ++u) {
+                const int j = j0 + u * SIL_THREADS;
+                if (j >= S) continue;
+                double v;
+                if (metric == PILOT_SIL_PRECOMPUTED) v = g[u];
+                else if (j == i) v = 0.0;
+                else if (metric == PILOT_METRIC_COSINE) {
+                    v = 1.0 - g[u] * ni * nj[u];
+                    v = v < 0.0 ? 0.0 : (v > 2.0 ? 2.0 : v);
+                } else {
+                    v = (ni + nj[u]) - 2.0 * g[u];
+                    v = v > 0.0 ? sqrt(v) : 0.0;
+                }
+                srow[j] = v;
+            }
+        }
         __syncthreads();
     }
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     for (int c = warp; c < L; c += SIL_THREADS / 32) {
         double s = 0.0;
         const int p1 = seg[c + 1];
-        for (int p = seg[c] + lane; p < p1; p += 32) s += STAGED ? srow[perm[p]] : dist(perm[p]);
+        if (STAGED) {
+            // lane-strided partial sums in a fixed order (batches of UB members: the perm loads are independent)
+            for (int p0 = seg[c] + lane; p0 < p1; p0 += 32 * UB) {
+                int q[UB];
+#pragma unroll
+                for (int u = 0; u < UB; ++u) q[u] = p0 + 32 * u < p1 ? perm[p0 + 32 * u] : -1;
+#pragma unroll
+                for (int u = 0; u < UB; ++u)
+                    if (q[u] >= 0) s += srow[q[u]];
+            }
+        } else {
+            for (int p = seg[c] + lane; p < p1; p += 32) s += dist(perm[p]);
+        }
         s = warp_sum_d(s);
         if (lane == 0) ssum[c] = s;
     }
