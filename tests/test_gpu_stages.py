@@ -140,6 +140,27 @@ def test_centroid_median_column_form_shapes(dtype, n, K, D):
         np.testing.assert_array_equal(cent2.cpu().numpy(), want.astype(dtype))
 
 
+def test_centroid_median_beyond_4gb():
+    """12 M cells x 96 dims of float32 = 4.6 GB: byte offsets beyond 2^32 and tens of chunks per CTA in the stream
+    pass.  The expectation is computed on the GPU (a full sort per type), exact like the kernel."""
+    n, K, D = 12_000_000, 3, 96
+    g = torch.Generator(device="cuda").manual_seed(7)
+    X = torch.randn((n, D), device="cuda", dtype=torch.float32, generator=g)
+    code = torch.randint(0, K, (n,), device="cuda", dtype=torch.int32, generator=g)
+    X += code[:, None].to(torch.float32) * 0.25
+    X[n - 1] = 1e6                                      # the very last row counts
+    cent, cent64 = ops.centroid_median(X, code, K)
+    assert ops.median_fallbacks(K, D) == 0
+    for k in range(K):
+        Xk = X[code == k]
+        m = Xk.shape[0]
+        srt = torch.sort(Xk, dim=0).values
+        want = srt[(m - 1) // 2] if m % 2 else (srt[m // 2 - 1] + srt[m // 2]) / 2
+        assert torch.equal(cent[k], want), k
+        assert torch.equal(cent64[k], want.to(torch.float64)), k
+        del Xk, srt
+
+
 @pytest.mark.parametrize("order", ["by_type", "by_type_blocks", "one_type_dominates"])
 def test_centroid_median_sorted_inputs_stay_on_the_fast_path(order):
     """AnnData objects are often sorted by cluster or by sample.  The run-form stream pass counting-sorts 4096-row
