@@ -242,6 +242,10 @@ def _stage_reset() -> None:
     _pinned_stage["used"] = 0
 
 
+_TORCH_DTYPE = {"int8": torch.int8, "int16": torch.int16, "int32": torch.int32, "int64": torch.int64,
+                "uint8": torch.uint8, "float32": torch.float32, "float64": torch.float64}
+
+
 def _to_device_staged(arr: np.ndarray) -> torch.Tensor:
     dev = _device()
     nbytes = (arr.nbytes + 255) // 256 * 256
@@ -253,7 +257,7 @@ def _to_device_staged(arr: np.ndarray) -> torch.Tensor:
         buf = torch.empty(max(nbytes * 2, 1 << 22), dtype=torch.uint8, pin_memory=True)
         _pinned_stage["buf"] = buf
     _pinned_stage["used"] = off + nbytes
-    host = buf[off:off + arr.nbytes].view(torch.from_numpy(arr).dtype).view(arr.shape)
+    host = buf[off:off + arr.nbytes].view(_TORCH_DTYPE[arr.dtype.name]).view(arr.shape)
     host.numpy()[...] = arr
     return host.to(dev, non_blocking=True)
 

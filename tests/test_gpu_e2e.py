@@ -66,6 +66,28 @@ def test_kidney_igan_real_data_golden():
     assert [str(x) for x in u["real_labels"]] == list(g["real_labels"])
 
 
+def test_categorical_columns_with_unused_categories():
+    """A cohort subset in scanpy keeps the categories of the full one: samples and cell types that no longer occur
+    must vanish from every output exactly as `.unique()` makes them vanish in the reference (Trajectory.py:402-425)."""
+    X, obs = synth.make_cells(60_000, 12, 9, 14, seed=8, labels="categorical")
+    keep = ~obs["sampleID"].isin(obs["sampleID"].cat.categories[[2, 9]]) & (obs["cell_types"] != obs["cell_types"].cat.categories[4])
+    obs2 = obs[keep.to_numpy()].copy()                    # categories untouched: 14 samples / 9 types declared
+    assert len(obs2["sampleID"].cat.categories) == 14 and obs2["sampleID"].nunique() == 12
+    adata = synth.FakeAnnData(obs2, obsm={"X_PCA": np.ascontiguousarray(X[keep.to_numpy()])})
+    tl.wasserstein_distance(adata, emb_matrix="X_PCA", clusters_col="cell_types", sample_col="sampleID", status="status")
+    annot, data = adata.uns["annot"], adata.uns["data"]
+    wprops = po.cluster_representations(annot)
+    assert len(wprops) == 12 and list(wprops.keys()) == list(adata.uns["proportions"].keys())
+    for k in wprops:
+        assert wprops[k].shape == (8,) and np.array_equal(wprops[k], adata.uns["proportions"][k])
+    wdis, wcost = po.cost_matrix(annot, data, "cosine")
+    assert adata.uns["cost"].shape == (8, 8)
+    np.testing.assert_allclose(adata.uns["cost"].to_numpy(), wdis, rtol=1e-12, atol=1e-15)
+    wEMD, _ = po.wasserstein_d(wprops, wdis / wdis.max())
+    np.testing.assert_allclose(adata.uns["EMD"], wEMD, rtol=1e-9, atol=1e-15)
+    assert adata.uns["real_labels"] == po.return_real_labels(annot)
+
+
 @pytest.mark.parametrize("labels", ["str", "categorical"])
 def test_config_c1_full(labels):
     """BASELINE configs[0]: 200K cells, 30-dim, 10 types, 20 samples, cosine, exact EMD."""
